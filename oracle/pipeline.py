@@ -1,0 +1,86 @@
+"""Oracle (TEST INFRASTRUCTURE ONLY): the whole `train_auto` separation of the stand-alone
+scripts, float64, structured exactly like the reference executes it -- per-frame STFT loop,
+patch copy loop, batches of 32 through the network, sequential cross-fade, one iSTFT per
+source.  This is both the parity checker for the CUDA pipeline and the timed CPU baseline.
+
+  DSD100   examples/dsd100/separate_dsd.py:239-313   (hanning, N=1024, overlap 25)
+  iKala    examples/ikala/separate_ikala.py:194-256  (hanning, N=1024, overlap 20, L+R)
+  Bach10   examples/bach10/separate_bach10.py:232-306 (blackmanharris, N=4096, overlap 25)
+  util patcher variant: examples/dsd100/trainCNN.py:300-333
+"""
+import numpy as np
+from . import dsp, patch, nets
+
+
+def decode_wav_array(audioObj, family="dsd"):
+    """int/float PCM array as returned by scipy.io.wavfile.read -> mono float64
+    (separate_dsd.py:277-287; iKala sums L+R without halving, separate_ikala.py:229)."""
+    try:
+        maxv = np.finfo(audioObj.dtype).max
+    except ValueError:
+        maxv = np.iinfo(audioObj.dtype).max
+    a = audioObj.astype('float') / maxv
+    if family == "ikala":
+        return a[:, 0] + a[:, 1]
+    if a.ndim > 1 and a.shape[1] > 1:
+        return (a[:, 0] + a[:, 1]) / 2
+    return a if a.ndim == 1 else a[:, 0]
+
+
+def separate(audio, params, arch, frameSize=1024, hopSize=512, window=np.hanning,
+             scale_factor=0.3, time_context=30, overlap=25, batch_size=32,
+             patcher="standalone", return_spec=False):
+    """mono float64 audio [L] (or, for arch 'bach10_score', a callable building the 4-channel
+    input from the scaled magnitude) -> stems float64 [nsrc, L]."""
+    a = nets.ARCHS[arch]
+    mag, ph = dsp.compute_file(audio, phase=True, frameSize=frameSize, hopSize=hopSize,
+                               window=window)
+    mag = scale_factor * mag.astype(np.float32)          # separate_dsd.py:290 (float32!)
+    gen = patch.generate_overlapadd if patcher == "standalone" else patch.generate_overlapadd_util
+    batches, nchunks = gen(mag, input_size=mag.shape[-1], time_context=time_context,
+                           overlap=overlap, batch_size=batch_size)
+    output = [nets.predict_function2(params, b, arch) for b in batches]
+    output = np.array(output)                            # [nb, nsrc, B, 1, tc, F]
+    if nchunks == 0:
+        mm = np.zeros((a["nsrc"], len(ph), mag.shape[-1]))
+    else:
+        mm = patch.overlapadd_multi(output, batches, nchunks, overlap=overlap)
+    stems = []
+    for i in range(a["nsrc"]):
+        m = mm[i, :len(ph)]
+        if m.shape[0] < len(ph):                          # cannot happen with the stock patchers
+            m = np.concatenate([m, np.zeros((len(ph) - m.shape[0], m.shape[1]))])
+        audio_out = dsp.compute_inverse(m / scale_factor, ph, frameSize=frameSize,
+                                        hopSize=hopSize, window=window)
+        if len(audio_out) > len(audio):
+            audio_out = audio_out[:len(audio)]
+        stems.append(audio_out)
+    stems = np.stack(stems)
+    if return_spec:
+        return stems, mag, ph, mm
+    return stems
+
+
+def synth_mixture(seconds, seed, sr=44100):
+    """Seeded synthetic 4-stem mixture: harmonic tone with vibrato,
+    low sine bursts, noise bursts, pink-ish noise; int16-quantised like a wav file.
+    Returns (mixture float64 [L], stems float64 [4, L])."""
+    rng = np.random.default_rng(seed)
+    L = int(round(seconds * sr))
+    t = np.arange(L) / sr
+    f0 = rng.uniform(110, 440)
+    vib = 1 + 0.01 * np.sin(2 * np.pi * 5 * t)
+    s1 = sum(np.sin(2 * np.pi * f0 * h * t * vib + rng.uniform(0, 6.28)) / h for h in range(1, 11))
+    fb = rng.uniform(55, 110)
+    s2 = np.sin(2 * np.pi * fb * t) * (np.sin(2 * np.pi * rng.uniform(1, 2) * t) > 0)
+    rate = rng.uniform(2, 4)
+    env = np.exp(-((t * rate) % 1.0) / (rate * 0.010))
+    s3 = rng.standard_normal(L) * env
+    w = rng.standard_normal(L)
+    s4 = np.cumsum(w) * 0.02
+    s4 = s4 - np.convolve(s4, np.ones(512) / 512, mode="same") + 0.3 * w
+    stems = np.stack([s1, s2, s3, s4])
+    stems *= 0.2 / np.maximum(np.abs(stems).max(axis=1, keepdims=True), 1e-12)
+    mix = stems.sum(axis=0)
+    mix = np.round(mix * 32767).astype(np.int16).astype('float') / 32767
+    return mix, stems
