@@ -1,0 +1,428 @@
+// api.cu -- C ABI of libdcs.so (include/dcs.h): context / workspace, STFT plans, model
+// re-layout + upload, and the host-side orchestration of the separation pipeline.
+#include <stdarg.h>
+#include <math.h>
+#include <string.h>
+#include <vector>
+#include "common.cuh"
+
+namespace dcs {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int DevBuf::ensure(size_t bytes, cudaStream_t stream, bool* grew) {
+  if (grew) *grew = false;
+  if (bytes <= cap) return DCS_OK;
+  if (p) {
+    DCS_CUDA(cudaStreamSynchronize(stream));
+    DCS_CUDA(cudaFree(p));
+    p = nullptr;
+    cap = 0;
+  }
+  size_t want = (bytes + (1u << 20) - 1) & ~((size_t)(1u << 20) - 1);
+  cudaError_t e = cudaMalloc(&p, want);
+  if (e != cudaSuccess) {
+    p = nullptr;
+    set_error("cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+    return DCS_ENOMEM;
+  }
+  cap = want;
+  DCS_CUDA(cudaMemsetAsync(p, 0, want, stream));
+  if (grew) *grew = true;
+  return DCS_OK;
+}
+
+void DevBuf::release() {
+  if (p) cudaFree(p);
+  p = nullptr;
+  cap = 0;
+}
+
+static int upload(const std::vector<float>& h, float** d) {
+  DCS_CUDA(cudaMalloc((void**)d, h.size() * sizeof(float)));
+  DCS_CUDA(cudaMemcpy(*d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return DCS_OK;
+}
+
+}  // namespace dcs
+
+using namespace dcs;
+
+int64_t dcs_ctx::workspace_bytes() const {
+  size_t s = audio.cap + X.cap + mag.cap + S.cap + stems.cap + pcm_in.cap + pcm_out.cap;
+  for (const auto& b : net) s += b.cap;
+  return (int64_t)s;
+}
+
+// ------------------------------------------------------------------------------------ model
+struct dcs_model {
+  dcs_ctx* ctx;
+  int arch, F, tc, nsrc;
+  // DSD dims
+  int C1, C2, kh2, h2, nfc, ndec;
+  int64_t ldw;
+  std::vector<float*> dev;  // owned device arrays
+  float *W1f, *b1, *W2c, *b2, *Wfc, *bfc, *Wdec, *bdec, *Wt2, *W1t, *bout;
+};
+
+extern "C" {
+
+int dcs_version(void) { return DCS_VERSION; }
+const char* dcs_last_error(void) { return g_err; }
+
+int dcs_create(int device, dcs_ctx** out) {
+  DCS_REQUIRE(out != nullptr, "dcs_create: out is NULL");
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    set_error("dcs_create: no usable CUDA device (%s); libdcs has no CPU fallback",
+              e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    return DCS_ECUDA;
+  }
+  DCS_REQUIRE(device >= 0 && device < n, "dcs_create: device %d out of range (%d devices)", device, n);
+  DCS_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  DCS_CUDA(cudaGetDeviceProperties(&prop, device));
+  DCS_REQUIRE(prop.major >= 10, "dcs_create: device %d is sm_%d%d; this library is built for sm_100a only", device,
+              prop.major, prop.minor);
+  dcs_ctx* c = new dcs_ctx();
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  *out = c;
+  return DCS_OK;
+}
+
+int dcs_destroy(dcs_ctx* c) {
+  if (!c) return DCS_OK;
+  cudaSetDevice(c->device);
+  c->audio.release(); c->X.release(); c->mag.release(); c->S.release(); c->stems.release();
+  c->pcm_in.release(); c->pcm_out.release();
+  for (auto& b : c->net) b.release();
+  delete c;
+  return DCS_OK;
+}
+
+int64_t dcs_workspace_bytes(const dcs_ctx* c) { return c ? c->workspace_bytes() : 0; }
+int64_t dcs_launch_count(const dcs_ctx* c) { return c ? c->launches : 0; }
+
+int dcs_profile(dcs_ctx* c, int enable) {
+  DCS_REQUIRE(c != nullptr, "dcs_profile: NULL ctx");
+  c->prof_on = enable != 0;
+  return DCS_OK;
+}
+
+int dcs_profile_read(dcs_ctx* c, char* names_buf, int names_len, float* ms, int max_n) {
+  DCS_REQUIRE(c && names_buf && ms && names_len > 0, "dcs_profile_read: bad argument");
+  int n = 0;
+  size_t pos = 0;
+  names_buf[0] = 0;
+  for (auto& r : c->prof) {
+    float t = 0.f;
+    if (n < max_n && cudaEventSynchronize(r.e1) == cudaSuccess && cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess) {
+      const size_t len = strlen(r.name);
+      if (pos + len + 2 < (size_t)names_len) {
+        memcpy(names_buf + pos, r.name, len);
+        pos += len;
+        names_buf[pos++] = '\n';
+        names_buf[pos] = 0;
+        ms[n++] = t;
+      }
+    }
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  c->prof.clear();
+  return n;
+}
+
+// ------------------------------------------------------------------------------------ STFT plan
+int64_t dcs_num_frames(int64_t L, int hop) { return (L + hop - 1) / hop + 2; }
+int64_t dcs_padded_bins(int N) { return ((int64_t)N / 2 + 1 + 7) / 8 * 8; }
+
+int dcs_stft_plan(dcs_ctx* ctx, int N, int hop, const double* window, const double* syn_window, dcs_stft** out) {
+  DCS_REQUIRE(ctx && window && out, "dcs_stft_plan: NULL argument");
+  DCS_REQUIRE(N == 256 || N == 512 || N == 1024 || N == 2048 || N == 4096, "frame size %d not in {256..4096}", N);
+  DCS_REQUIRE(hop > 0 && hop <= N && hop % 2 == 0, "hop %d must be even and in (0, %d]", hop, N);
+  DCS_CUDA(cudaSetDevice(ctx->device));
+  if (!syn_window) syn_window = window;
+  std::vector<float> w(N), ws(N), w2(N), tw(2 * (size_t)N);
+  for (int i = 0; i < N; ++i) {
+    w[i] = (float)window[i];
+    ws[i] = (float)syn_window[i];
+    w2[i] = (float)(window[i] * syn_window[i]);
+    const double a = -2.0 * M_PI * (double)i / (double)N;
+    tw[2 * i] = (float)cos(a);
+    tw[2 * i + 1] = (float)sin(a);
+  }
+  dcs_stft* p = new dcs_stft();
+  p->ctx = ctx; p->N = N; p->hop = hop;
+  p->d_win = p->d_wsyn = p->d_w2 = nullptr; p->d_tw = nullptr;
+  int r = upload(w, &p->d_win);
+  if (r == DCS_OK) r = upload(ws, &p->d_wsyn);
+  if (r == DCS_OK) r = upload(w2, &p->d_w2);
+  if (r == DCS_OK) r = upload(tw, (float**)&p->d_tw);
+  if (r != DCS_OK) { dcs_stft_plan_destroy(p); return r; }
+  *out = p;
+  return DCS_OK;
+}
+
+int dcs_stft_plan_destroy(dcs_stft* p) {
+  if (!p) return DCS_OK;
+  cudaFree(p->d_win); cudaFree(p->d_wsyn); cudaFree(p->d_w2); cudaFree(p->d_tw);
+  delete p;
+  return DCS_OK;
+}
+
+int dcs_stft_forward(dcs_stft* p, const float* d_audio, int64_t L, dcs_complex* d_X, float* d_mag, float mag_scale,
+                     int64_t ldf, void* stream) {
+  DCS_REQUIRE(p && d_audio && L > 0, "dcs_stft_forward: bad argument");
+  return launch_stft(p, d_audio, L, (float2*)d_X, d_mag, nullptr, mag_scale, ldf, (cudaStream_t)stream);
+}
+
+int dcs_stft_forward_polar(dcs_stft* p, const float* d_audio, int64_t L, float* d_mag, float* d_phase, float mag_scale,
+                           int64_t ldf, void* stream) {
+  DCS_REQUIRE(p && d_audio && L > 0, "dcs_stft_forward_polar: bad argument");
+  return launch_stft(p, d_audio, L, nullptr, d_mag, d_phase, mag_scale, ldf, (cudaStream_t)stream);
+}
+
+int dcs_istft(dcs_stft* p, const dcs_complex* d_S, int nsrc, int64_t T, int64_t ldf, int64_t src_stride, float* d_out,
+              int64_t Lout, int64_t out_stride, void* stream) {
+  DCS_REQUIRE(p && d_S && d_out && T > 0, "dcs_istft: bad argument");
+  return launch_istft(p, (const float2*)d_S, nullptr, nullptr, 1.f, nsrc, T, ldf, src_stride, d_out, Lout, out_stride,
+                      (cudaStream_t)stream);
+}
+
+int dcs_istft_polar(dcs_stft* p, dcs_ctx* ctx, const float* d_mag, const float* d_phase, float mag_scale, int64_t T,
+                    int64_t ldf, float* d_out, int64_t Lout, void* stream) {
+  DCS_REQUIRE(p && d_mag && d_phase && d_out && T > 0, "dcs_istft_polar: bad argument");
+  (void)ctx;
+  return launch_istft(p, nullptr, d_mag, d_phase, mag_scale * sqrtf((float)p->N), 1, T, ldf, 0, d_out, Lout, Lout,
+                      (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------ model
+int64_t dcs_num_patches(int64_t T, int tc, int overlap, int patcher) {
+  const int64_t step = tc - overlap;
+  if (step <= 0) return 0;
+  const int64_t lim = patcher == DCS_PATCHER_UTIL ? overlap : tc;
+  if (T <= lim) return 0;
+  return (T - lim - 1) / step + 1;
+}
+
+int dcs_model_nsources(const dcs_model* m) { return m ? m->nsrc : 0; }
+
+int dcs_model_destroy(dcs_model* m) {
+  if (!m) return DCS_OK;
+  for (float* d : m->dev) cudaFree(d);
+  delete m;
+  return DCS_OK;
+}
+
+static bool shape_is(const int64_t* s, int nd, int want_nd, int64_t a, int64_t b = 1, int64_t c = 1, int64_t d = 1) {
+  return nd == want_nd && s[0] == a && s[1] == b && s[2] == c && s[3] == d;
+}
+
+static int model_create_dsd(dcs_model* m, int nparams, const float* const* hp, const int64_t* shp, const int* nd) {
+  const int F = m->F, tc = m->tc;
+  const int C1 = 50, C2 = 50, nfc = 128, kh2 = tc / 2, h2 = tc - kh2 + 1, flat = C2 * h2, ndec = 3;
+  m->C1 = C1; m->C2 = C2; m->kh2 = kh2; m->h2 = h2; m->nfc = nfc; m->ndec = ndec; m->nsrc = 4;
+  if (nparams != 15) { set_error("DSD model needs 15 parameter arrays, got %d (SURVEY.md App. A.4)", nparams); return DCS_EMODEL; }
+  const bool ok = shape_is(shp + 0, nd[0], 4, C1, 1, 1, F) && shape_is(shp + 4, nd[1], 1, C1) &&
+                  shape_is(shp + 8, nd[2], 1, C1) && shape_is(shp + 12, nd[3], 4, C2, C1, kh2, 1) &&
+                  shape_is(shp + 16, nd[4], 1, C2) && shape_is(shp + 20, nd[5], 1, C2) &&
+                  shape_is(shp + 24, nd[6], 2, flat, nfc) && shape_is(shp + 28, nd[7], 1, nfc) &&
+                  shape_is(shp + 32, nd[8], 2, nfc, flat) && shape_is(shp + 36, nd[9], 1, flat) &&
+                  shape_is(shp + 40, nd[10], 2, nfc, flat) && shape_is(shp + 44, nd[11], 1, flat) &&
+                  shape_is(shp + 48, nd[12], 2, nfc, flat) && shape_is(shp + 52, nd[13], 1, flat) &&
+                  shape_is(shp + 56, nd[14], 1, 4);
+  if (!ok) { set_error("DSD parameter shapes do not match feat_size=%d time_context=%d", F, tc); return DCS_EMODEL; }
+  const int64_t ldf = dcs_padded_bins(2 * (F - 1));
+  m->ldw = ldf;
+  const float *W1 = hp[0], *W2 = hp[3], *Wfc = hp[6];
+  std::vector<float> W1f((size_t)ldf * C1, 0.f), W1t((size_t)C1 * ldf, 0.f), b1(C1), W2c((size_t)kh2 * C1 * C2),
+      Wt2((size_t)kh2 * C2 * C1), b2(C2), Wfcp((size_t)flat * nfc), Wdec((size_t)nfc * ndec * flat), bdec((size_t)ndec * flat);
+  for (int f = 0; f < C1; ++f)
+    for (int b = 0; b < F; ++b) {
+      const float v = W1[(size_t)f * F + (F - 1 - b)];  // flip_filters
+      W1f[(size_t)b * C1 + f] = v;
+      W1t[(size_t)f * ldf + b] = v;
+    }
+  for (int f = 0; f < C1; ++f) b1[f] = hp[1][f] + hp[2][f];
+  for (int f = 0; f < C2; ++f) b2[f] = hp[4][f] + hp[5][f];
+  for (int f = 0; f < C2; ++f)
+    for (int c = 0; c < C1; ++c)
+      for (int q = 0; q < kh2; ++q) {
+        const float v = W2[((size_t)f * C1 + c) * kh2 + q];
+        W2c[((size_t)(kh2 - 1 - q) * C1 + c) * C2 + f] = v;  // conv2 forward, tap p' = kh2-1-q
+        Wt2[((size_t)q * C2 + f) * C1 + c] = v;              // InverseLayer(conv2)
+      }
+  for (int f = 0; f < C2; ++f)
+    for (int i = 0; i < h2; ++i)
+      memcpy(&Wfcp[((size_t)i * C2 + f) * nfc], &Wfc[((size_t)f * h2 + i) * nfc], nfc * sizeof(float));
+  for (int d = 0; d < ndec; ++d) {
+    const float* Wd = hp[8 + 2 * d];
+    const float* bd = hp[9 + 2 * d];
+    for (int f = 0; f < C2; ++f)
+      for (int i = 0; i < h2; ++i) {
+        const size_t col = (size_t)d * flat + (size_t)i * C2 + f;
+        bdec[col] = bd[f * h2 + i];
+        for (int o = 0; o < nfc; ++o) Wdec[(size_t)o * ndec * flat + col] = Wd[(size_t)o * flat + f * h2 + i];
+      }
+  }
+  std::vector<float> bout(hp[14], hp[14] + 4), bfc(hp[7], hp[7] + nfc);
+  struct { const std::vector<float>* h; float** d; } ups[] = {
+      {&W1f, &m->W1f}, {&b1, &m->b1}, {&W2c, &m->W2c}, {&b2, &m->b2}, {&Wfcp, &m->Wfc}, {&bfc, &m->bfc},
+      {&Wdec, &m->Wdec}, {&bdec, &m->bdec}, {&Wt2, &m->Wt2}, {&W1t, &m->W1t}, {&bout, &m->bout}};
+  for (auto& u : ups) {
+    DCS_TRY(upload(*u.h, u.d));
+    m->dev.push_back(*u.d);
+  }
+  return DCS_OK;
+}
+
+int dcs_model_create(dcs_ctx* ctx, int arch, int feat_size, int time_context, int nparams, const float* const* h_params,
+                     const int64_t* shapes, const int* ndims, dcs_model** out) {
+  DCS_REQUIRE(ctx && h_params && shapes && ndims && out, "dcs_model_create: NULL argument");
+  DCS_REQUIRE(feat_size >= 3 && ((feat_size - 1) & (feat_size - 2)) == 0, "feat_size %d is not 2^k+1", feat_size);
+  DCS_REQUIRE(time_context >= 4 && time_context <= 64, "time_context %d out of range", time_context);
+  DCS_CUDA(cudaSetDevice(ctx->device));
+  dcs_model* m = new dcs_model();
+  m->ctx = ctx; m->arch = arch; m->F = feat_size; m->tc = time_context;
+  int r;
+  switch (arch) {
+    case DCS_ARCH_DSD: r = model_create_dsd(m, nparams, h_params, shapes, ndims); break;
+    default:
+      set_error("dcs_model_create: architecture %d has no CUDA path yet", arch);
+      r = DCS_EINVAL;
+  }
+  if (r != DCS_OK) { dcs_model_destroy(m); return r; }
+  *out = m;
+  return DCS_OK;
+}
+
+// ------------------------------------------------------------------------------------ pipeline
+static int dsd_forward(dcs_ctx* ctx, dcs_model* m, const float* d_mag, const float2* d_X, int64_t T, int64_t ldf,
+                       int overlap, int patcher, float2* d_S, int64_t src_stride, cudaStream_t st) {
+  const int tc = m->tc, step = tc - overlap, C1 = m->C1, C2 = m->C2, kh2 = m->kh2, h2 = m->h2, nfc = m->nfc;
+  const int64_t P = dcs_num_patches(T, tc, overlap, patcher);
+  if (P == 0) {  // clip shorter than one patch: nothing is predicted, every stem is silence
+    for (int s = 0; s < m->nsrc; ++s) DCS_CUDA(cudaMemsetAsync(d_S + s * src_stride, 0, (size_t)T * ldf * sizeof(float2), st));
+    return DCS_OK;
+  }
+  DCS_REQUIRE(P * 3 * tc < (int64_t)1 << 31, "clip too long (%lld patches)", (long long)P);
+  const int64_t Tp = std::max<int64_t>(T, (P - 1) * step + tc);
+  const int HP = h2 + 2 * (kh2 - 1), ldg = (C1 + 3) / 4 * 4;
+  DevBuf &bH1 = ctx->net[0], &bH2 = ctx->net[1], &bz = ctx->net[2], &bap = ctx->net[3], &bG = ctx->net[4];
+  DCS_TRY(bH1.ensure((size_t)Tp * C1 * 4, st));
+  DCS_TRY(bH2.ensure((size_t)(Tp - kh2 + 1) * C2 * 4, st));
+  DCS_TRY(bz.ensure((size_t)P * nfc * 4, st));
+  DCS_TRY(bap.ensure((size_t)P * 3 * HP * C2 * 4, st));  // zero on (re)allocation; only the interior is ever written
+  DCS_TRY(bG.ensure((size_t)P * 3 * tc * ldg * 4, st));
+  float *H1 = bH1.as<float>(), *H2 = bH2.as<float>(), *z = bz.as<float>(), *ap = bap.as<float>(), *G = bG.as<float>();
+
+  // conv1 + both biases, once per frame (kernel height 1): H1[Tp][C1] = mag[T][F] * W1f
+  GemmDesc g1 = gemm_plain(d_mag, ldf, m->W1f, C1, m->b1, H1, C1, (int)Tp, C1, m->F, 0);
+  g1.a_valid_rows = (int)T;  // util patcher: frames beyond T are zero input
+  { ProfScope ps(ctx, "enc_conv1_gemm", st); DCS_TRY(launch_gemm(ctx, g1, st)); }
+  // conv2 + both biases, once per frame offset: rows overlap in H1 (stride C1, length kh2*C1)
+  GemmDesc g2 = gemm_plain(H1, C1, m->W2c, C2, m->b2, H2, C2, (int)(Tp - kh2 + 1), C2, kh2 * C1, 0);
+  { ProfScope ps(ctx, "enc_conv2_gemm", st); DCS_TRY(launch_gemm(ctx, g2, st)); }
+  // bottleneck: patch k reads H2 rows k*step .. k*step+h2-1 (contiguous h2*C2 floats)
+  GemmDesc g3 = gemm_plain(H2, (int64_t)step * C2, m->Wfc, nfc, m->bfc, z, nfc, (int)P, nfc, h2 * C2, 1);
+  { ProfScope ps(ctx, "bottleneck_gemm", st); DCS_TRY(launch_gemm(ctx, g3, st)); }
+  // three decoder dense layers side by side, scattered into the zero-padded buffer
+  GemmDesc g4 = gemm_plain(z, nfc, m->Wdec, 3 * h2 * C2, m->bdec, ap, (int64_t)3 * HP * C2, (int)P, 3 * h2 * C2, nfc, 1);
+  g4.n_seg = h2 * C2; g4.n_ss = (int64_t)HP * C2; g4.c_col0 = (int64_t)(kh2 - 1) * C2;
+  { ProfScope ps(ctx, "dec_dense_gemm", st); DCS_TRY(launch_gemm(ctx, g4, st)); }
+  // InverseLayer(conv2): full correlation on the padded activations, rows (k, d, u)
+  GemmDesc g5 = gemm_plain(ap, 0, m->Wt2, C1, nullptr, G, ldg, (int)(P * 3 * tc), C1, kh2 * C2, 0);
+  g5.m_inner = tc; g5.a_so = (int64_t)HP * C2; g5.a_si = C2;
+  { ProfScope ps(ctx, "dec_convT2_gemm", st); DCS_TRY(launch_gemm(ctx, g5, st)); }
+  // InverseLayer(conv1) + bias + ReLU + mask + cross-fade + phase
+  DsdMaskArgs a;
+  a.G = G; a.ldg = ldg; a.W1t = m->W1t; a.ldw = (int)m->ldw; a.bout = m->bout; a.X = d_X; a.S = d_S;
+  a.ldf = ldf; a.src_stride = src_stride; a.T = (int)T; a.P = (int)P; a.tc = tc; a.overlap = overlap; a.F = m->F;
+  ProfScope ps(ctx, "dec_convT1_mask_xfade", st);
+  return launch_dsd_mask(ctx, a, st);
+}
+
+int dcs_separate_spec(dcs_ctx* ctx, dcs_model* m, const float* d_mag, const dcs_complex* d_X, int64_t T, int64_t ldf,
+                      int overlap, int patcher, dcs_complex* d_S, int64_t src_stride, void* stream) {
+  DCS_REQUIRE(ctx && m && d_mag && d_X && d_S, "dcs_separate_spec: NULL argument");
+  DCS_REQUIRE(T > 0 && ldf >= m->F && src_stride >= T * ldf, "dcs_separate_spec: bad shape");
+  DCS_REQUIRE(overlap >= 0 && overlap < m->tc, "overlap %d must be in [0, time_context=%d)", overlap, m->tc);
+  DCS_REQUIRE(patcher == DCS_PATCHER_STANDALONE || patcher == DCS_PATCHER_UTIL, "unknown patcher %d", patcher);
+  DCS_CUDA(cudaSetDevice(ctx->device));
+  switch (m->arch) {
+    case DCS_ARCH_DSD:
+      return dsd_forward(ctx, m, d_mag, (const float2*)d_X, T, ldf, overlap, patcher, (float2*)d_S, src_stride,
+                         (cudaStream_t)stream);
+  }
+  DCS_REQUIRE(false, "architecture %d has no CUDA path yet", m->arch);
+}
+
+int dcs_separate_audio(dcs_ctx* ctx, dcs_model* m, dcs_stft* p, const float* d_audio, int64_t L, float scale_factor,
+                       int overlap, int patcher, float* d_stems, int64_t stem_stride, void* stream) {
+  DCS_REQUIRE(ctx && m && p && d_audio && d_stems, "dcs_separate_audio: NULL argument");
+  DCS_REQUIRE(L > 0 && stem_stride >= L, "dcs_separate_audio: bad length");
+  DCS_REQUIRE(p->N / 2 + 1 == m->F, "frame size %d does not give the model's %d bins", p->N, m->F);
+  cudaStream_t st = (cudaStream_t)stream;
+  DCS_CUDA(cudaSetDevice(ctx->device));
+  const int64_t T = dcs_num_frames(L, p->hop), ldf = dcs_padded_bins(p->N);
+  DCS_TRY(ctx->X.ensure((size_t)T * ldf * sizeof(float2), st));
+  DCS_TRY(ctx->mag.ensure((size_t)T * ldf * sizeof(float), st));
+  DCS_TRY(ctx->S.ensure((size_t)m->nsrc * T * ldf * sizeof(float2), st));
+  float2* X = ctx->X.as<float2>();
+  float* mag = ctx->mag.as<float>();
+  float2* S = ctx->S.as<float2>();
+  { ProfScope ps(ctx, "stft_fwd", st); DCS_TRY(launch_stft(p, d_audio, L, X, mag, nullptr, scale_factor, ldf, st)); }
+  DCS_TRY(dcs_separate_spec(ctx, m, mag, (const dcs_complex*)X, T, ldf, overlap, patcher, (dcs_complex*)S, T * ldf, stream));
+  ProfScope ps(ctx, "istft_ola", st);
+  return launch_istft(p, S, nullptr, nullptr, 1.f, m->nsrc, T, ldf, T * ldf, d_stems, L, stem_stride, st);
+}
+
+int dcs_separate_host(dcs_ctx* ctx, dcs_model* m, dcs_stft* p, const float* h_audio, int64_t L, float scale_factor,
+                      int overlap, int patcher, float* h_stems, int64_t stem_stride, void* stream) {
+  DCS_REQUIRE(ctx && m && h_audio && h_stems && L > 0 && stem_stride >= L, "dcs_separate_host: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  DCS_CUDA(cudaSetDevice(ctx->device));
+  DCS_TRY(ctx->audio.ensure((size_t)L * sizeof(float), st));
+  DCS_TRY(ctx->stems.ensure((size_t)m->nsrc * L * sizeof(float), st));
+  DCS_CUDA(cudaMemcpyAsync(ctx->audio.p, h_audio, (size_t)L * sizeof(float), cudaMemcpyHostToDevice, st));
+  DCS_TRY(dcs_separate_audio(ctx, m, p, ctx->audio.as<float>(), L, scale_factor, overlap, patcher, ctx->stems.as<float>(), L, stream));
+  DCS_CUDA(cudaMemcpy2DAsync(h_stems, (size_t)stem_stride * sizeof(float), ctx->stems.p, (size_t)L * sizeof(float),
+                             (size_t)L * sizeof(float), m->nsrc, cudaMemcpyDeviceToHost, st));
+  DCS_CUDA(cudaStreamSynchronize(st));
+  return DCS_OK;
+}
+
+int dcs_separate_pcm16_host(dcs_ctx* ctx, dcs_model* m, dcs_stft* p, const int16_t* h_pcm, int64_t L, int channels,
+                            int downmix, float scale_factor, int overlap, int patcher, int16_t* h_out,
+                            int64_t out_stride, void* stream) {
+  DCS_REQUIRE(ctx && m && h_pcm && h_out && L > 0 && out_stride >= L, "dcs_separate_pcm16_host: bad argument");
+  DCS_REQUIRE(channels >= 1 && channels <= 8 && downmix >= 0 && downmix <= 2, "bad channels/downmix");
+  DCS_REQUIRE(downmix == 0 || channels >= 2 || channels == 1, "downmix needs two channels");
+  cudaStream_t st = (cudaStream_t)stream;
+  DCS_CUDA(cudaSetDevice(ctx->device));
+  DCS_TRY(ctx->pcm_in.ensure((size_t)L * channels * sizeof(int16_t), st));
+  DCS_TRY(ctx->pcm_out.ensure((size_t)m->nsrc * L * sizeof(int16_t), st));
+  DCS_TRY(ctx->audio.ensure((size_t)L * sizeof(float), st));
+  DCS_TRY(ctx->stems.ensure((size_t)m->nsrc * L * sizeof(float), st));
+  DCS_CUDA(cudaMemcpyAsync(ctx->pcm_in.p, h_pcm, (size_t)L * channels * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+  DCS_TRY(launch_pcm_decode(ctx, ctx->pcm_in.as<int16_t>(), L, channels, downmix, ctx->audio.as<float>(), st));
+  DCS_TRY(dcs_separate_audio(ctx, m, p, ctx->audio.as<float>(), L, scale_factor, overlap, patcher, ctx->stems.as<float>(), L, stream));
+  DCS_TRY(launch_pcm_encode(ctx, ctx->stems.as<float>(), L, m->nsrc, L, ctx->pcm_out.as<int16_t>(), L, st));
+  DCS_CUDA(cudaMemcpy2DAsync(h_out, (size_t)out_stride * sizeof(int16_t), ctx->pcm_out.p, (size_t)L * sizeof(int16_t),
+                             (size_t)L * sizeof(int16_t), m->nsrc, cudaMemcpyDeviceToHost, st));
+  DCS_CUDA(cudaStreamSynchronize(st));
+  return DCS_OK;
+}
+
+}  // extern "C"

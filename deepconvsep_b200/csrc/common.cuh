@@ -1,0 +1,137 @@
+// common.cuh -- shared helpers for libdcs (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/dcs.h"
+
+namespace dcs {
+
+void set_error(const char* fmt, ...);
+
+#define DCS_CUDA(expr)                                                                  \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      dcs::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return DCS_ECUDA;                                                                 \
+    }                                                                                   \
+  } while (0)
+
+#define DCS_CHECK_LAUNCH()  DCS_CUDA(cudaGetLastError())
+
+#define DCS_REQUIRE(cond, ...)                 \
+  do {                                         \
+    if (!(cond)) {                             \
+      dcs::set_error(__VA_ARGS__);             \
+      return DCS_EINVAL;                       \
+    }                                          \
+  } while (0)
+
+#define DCS_TRY(expr)            \
+  do {                           \
+    int _r = (expr);             \
+    if (_r != DCS_OK) return _r; \
+  } while (0)
+
+__host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// grow-only device buffer; newly allocated memory is zero-filled
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes, cudaStream_t stream, bool* grew = nullptr);
+  void release();
+  template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace dcs
+
+struct dcs_prof_rec {
+  const char* name;
+  cudaEvent_t e0, e1;
+};
+
+struct dcs_ctx {
+  int device = 0;
+  int num_sms = 148;
+  int64_t launches = 0;
+  bool prof_on = false;
+  std::vector<dcs_prof_rec> prof;
+  // workspace of one in-flight pipeline
+  dcs::DevBuf audio, X, mag, S, stems, pcm_in, pcm_out;
+  dcs::DevBuf net[12];
+  int64_t workspace_bytes() const;
+};
+
+struct dcs_stft {
+  dcs_ctx* ctx;
+  int N, hop;
+  float* d_win;    // analysis window  float[N]
+  float* d_wsyn;   // synthesis window float[N]
+  float* d_w2;     // wsyn * win       float[N]
+  float2* d_tw;    // exp(-2*pi*i*q/N), q < N
+};
+
+namespace dcs {
+// records a pair of CUDA events around a pipeline stage when profiling is enabled on the ctx
+struct ProfScope {
+  dcs_ctx* c; cudaStream_t st; int idx;
+  ProfScope(dcs_ctx* ctx, const char* name, cudaStream_t s) : c(ctx), st(s), idx(-1) {
+    if (!c || !c->prof_on) return;
+    dcs_prof_rec r; r.name = name;
+    if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+    cudaEventRecord(r.e0, st);
+    c->prof.push_back(r);
+    idx = (int)c->prof.size() - 1;
+  }
+  ~ProfScope() { if (idx >= 0) cudaEventRecord(c->prof[idx].e1, st); }
+};
+}  // namespace dcs
+
+// ---- kernel launchers (each returns a DCS_* code) ---------------------------------------------
+namespace dcs {
+
+int launch_stft(dcs_stft* plan, const float* d_audio, int64_t L, float2* d_X, float* d_mag,
+                float* d_phase, float mag_scale, int64_t ldf, cudaStream_t st);
+int launch_istft(dcs_stft* plan, const float2* d_S, const float* d_mag, const float* d_phase,
+                 float polar_scale, int nsrc, int64_t T, int64_t ldf, int64_t src_stride, float* d_out,
+                 int64_t Lout, int64_t out_stride, cudaStream_t st);
+
+// generic strided-operand GEMM  C = act(A*B + bias)
+struct GemmDesc {
+  const float* A; const float* B; const float* bias; float* C;
+  int M, N, K;
+  int a_valid_rows;          // rows >= a_valid_rows of A read as zeros
+  int m_inner; int64_t a_so, a_si;   // A row offset  = (m / m_inner) * a_so + (m % m_inner) * a_si
+  int k_seg; int64_t k_ss;           // A col offset  = (k / k_seg) * k_ss + (k % k_seg)
+  int64_t ldb;                       // B[k][n] at B + k*ldb + n
+  int cm_inner; int64_t c_so, c_si;  // C row offset
+  int n_seg; int64_t n_ss, c_col0;   // C col offset  = c_col0 + (n / n_seg) * n_ss + (n % n_seg)
+  int relu;
+};
+GemmDesc gemm_plain(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C,
+                    int64_t ldc, int M, int N, int K, int relu);
+int launch_gemm(dcs_ctx* ctx, const GemmDesc& d, cudaStream_t st);
+
+struct DsdMaskArgs {
+  const float* G;      // [P][3][tc][ldg]  decoder activations after the transposed conv2
+  int ldg;
+  const float* W1t;    // [50][ldw]  W1t[c][b] = conv1.W[c,0,0,F-1-b]
+  int ldw;
+  const float* bout;   // [4]
+  const float2* X;     // [T][ldf]
+  float2* S;           // [4][T][ldf]
+  int64_t ldf, src_stride;
+  int T, P, tc, overlap, F;
+};
+int launch_dsd_mask(dcs_ctx* ctx, const DsdMaskArgs& a, cudaStream_t st);
+
+int launch_pcm_decode(dcs_ctx* ctx, const int16_t* d_pcm, int64_t L, int channels, int downmix, float* d_audio,
+                      cudaStream_t st);
+int launch_pcm_encode(dcs_ctx* ctx, const float* d_stems, int64_t L, int nsrc, int64_t stem_stride, int16_t* d_out,
+                      int64_t out_stride, cudaStream_t st);
+
+}  // namespace dcs

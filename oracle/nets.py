@@ -64,17 +64,22 @@ def param_shapes(arch, F, tc=30):
     return shp
 
 
-def make_synthetic_params(arch, F, tc=30, seed=0, dtype=np.float32):
-    """Seeded stand-in for a trained .pkl: Lasagne GlorotUniform weights, U(+-0.1) biases."""
+def make_synthetic_params(arch, F, tc=30, seed=0, dtype=np.float32, out_bias=0.002):
+    """Seeded stand-in for a trained .pkl: Lasagne GlorotUniform weights, U(+-0.1) biases.
+    The final per-source bias is U(+-out_bias): with Glorot weights the decoder output has a
+    standard deviation of ~2.5e-3 for |x| ~ 1e-2, so a +-0.1 output bias would swamp it and
+    every mask would be a constant -- a parity test that exercises nothing.  +-0.002 gives
+    ~50 % ReLU zeros per source, strongly varying masks and some all-zero bins."""
     rng = np.random.default_rng(seed)
     out = []
-    for s in param_shapes(arch, F, tc):
+    shapes = param_shapes(arch, F, tc)
+    for i, s in enumerate(shapes):
         if len(s) == 4:
             a = np.sqrt(6.0 / ((s[0] + s[1]) * s[2] * s[3]))
         elif len(s) == 2:
             a = np.sqrt(6.0 / (s[0] + s[1]))
         else:
-            a = 0.1
+            a = out_bias if i == len(shapes) - 1 else 0.1
         out.append(rng.uniform(-a, a, size=s).astype(dtype))
     return out
 

@@ -1,0 +1,129 @@
+"""GPU parity of the DSD100 separation path (through the C ABI) against the float64 oracle.
+
+Tolerance (BASELINE.json north_star): per-stem relative L2 on the float waveform <= 1e-4;
+SDR delta vs the synthetic ground-truth stems <= 0.01 dB."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import dsp, nets, pipeline, patch  # noqa: E402
+
+TOL = 1e-4
+
+
+def rel(a, b):
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def sdr(ref, est):
+    return 10 * np.log10(np.sum(ref ** 2) / max(np.sum((ref - est) ** 2), 1e-30))
+
+
+def make_sep(N, seed=0, overlap=25, patcher="standalone", window="hanning", hop=512):
+    from deepconvsep_b200.engine import Separator
+    F = N // 2 + 1
+    params = nets.make_synthetic_params("dsd", F, seed=seed)
+    return params, Separator(params, frame_size=N, hop=hop, window=window, overlap=overlap, patcher=patcher)
+
+
+@pytest.mark.parametrize("N,seconds,overlap,patcher", [
+    (1024, 4.0, 25, "standalone"), (2048, 3.0, 25, "standalone"), (1024, 2.5, 25, "util"),
+    (1024, 2.0, 20, "standalone"), (1024, 1.3, 10, "util"), (512, 1.0, 25, "standalone")])
+def test_separate_matches_oracle(N, seconds, overlap, patcher):
+    hop = min(512, N // 2)
+    params, sep = make_sep(N, seed=N + overlap, overlap=overlap, patcher=patcher, hop=hop)
+    mix, stems = pipeline.synth_mixture(seconds, 1000 + N)
+    want = pipeline.separate(mix, params, "dsd", frameSize=N, hopSize=hop, window=np.hanning, overlap=overlap,
+                             patcher=patcher)
+    got = sep.separate(mix)
+    assert got.shape == want.shape and got.dtype == np.float32
+    # the synthetic weights must exercise every source (no constant masks)
+    assert min(np.linalg.norm(want[s]) for s in range(4)) > 0.02 * np.linalg.norm(mix)
+    for s in range(4):
+        e = rel(got[s].astype(np.float64), want[s])
+        assert e <= TOL, (s, e)
+        assert abs(sdr(stems[s], got[s]) - sdr(stems[s], want[s])) <= 0.01
+    # the device-buffer entry point gives the same bits as the host-buffer one
+    d = sep.separate_device(torch.tensor(mix, dtype=torch.float32, device="cuda"))
+    assert np.array_equal(d.cpu().numpy(), got)
+
+
+def test_spec_level_matches_oracle():
+    """dcs_separate_spec: blended masked spectra vs overlapadd_multi(predict(...)) of the oracle."""
+    N, F = 1024, 513
+    params, sep = make_sep(N, seed=7)
+    mix, _ = pipeline.synth_mixture(3.0, 77)
+    _, mag, ph, mm = pipeline.separate(mix, params, "dsd", frameSize=N, overlap=25, return_spec=True)
+    X = dsp.stft_norm(mix, window=np.hanning(N), hopsize=512.0, nfft=float(N))
+    T = X.shape[0]
+    ldf = sep.stft.ldf
+    magd = torch.zeros((T, ldf), dtype=torch.float32, device="cuda")
+    Xd = torch.zeros((T, ldf), dtype=torch.complex64, device="cuda")
+    magd[:, :F] = torch.tensor(mag, device="cuda")
+    Xd[:, :F] = torch.tensor(X.astype(np.complex64), device="cuda")
+    S = sep.separate_spec(magd, Xd).cpu().numpy()[:, :, :F].astype(np.complex128)
+    want = (mm[:, :T] / 0.3) * np.sqrt(N) * np.exp(1j * ph)[None]
+    for s in range(4):
+        assert rel(S[s], want[s]) <= TOL, (s, rel(S[s], want[s]))
+    # frames past the last patch are exactly zero (stand-alone patcher drops the tail)
+    P = patch.num_patches(T, 30, 25)
+    assert sep.num_patches(T) == P
+    assert np.all(S[:, (P - 1) * 5 + 30:] == 0)
+
+
+@pytest.mark.parametrize("L", [1, 100, 14336, 14848, 15361])
+def test_short_and_edge_lengths(L):
+    """T <= time_context gives no patch (all-zero stems); T = 31, 32 give exactly one."""
+    N = 1024
+    params, sep = make_sep(N, seed=3)
+    rng = np.random.default_rng(L)
+    x = rng.standard_normal(L) * 0.1
+    got = sep.separate(x)
+    T = dsp.num_frames(L, 512)
+    if patch.num_patches(T, 30, 25) == 0:
+        assert np.all(got == 0)
+    else:
+        want = pipeline.separate(x, params, "dsd", frameSize=N, overlap=25)
+        for s in range(4):
+            assert rel(got[s].astype(np.float64), want[s]) <= TOL
+
+
+def test_pcm16_wav_contract():
+    """int16 stereo in -> (L+R)/2 downmix -> int16 stems out, as train_auto reads/writes wavs."""
+    N = 1024
+    params, sep = make_sep(N, seed=11)
+    mix, _ = pipeline.synth_mixture(2.0, 5)
+    rng = np.random.default_rng(0)
+    left = np.round(mix * 32767 * 0.9).astype(np.int16)
+    right = np.round((mix * 0.7 + 0.01 * rng.standard_normal(mix.size)) * 32767).astype(np.int16)
+    pcm = np.stack([left, right], axis=1)
+    mono = pipeline.decode_wav_array(pcm, "dsd")
+    want = pipeline.separate(mono, params, "dsd", frameSize=N, overlap=25)
+    want16 = (want * 32767).astype("int16")
+    got16 = sep.separate_pcm16(pcm)
+    assert got16.shape == want16.shape and got16.dtype == np.int16
+    d = got16.astype(np.int32) - want16.astype(np.int32)
+    assert np.abs(d).max() <= 1                      # truncation flips at most one LSB
+    assert np.mean(d != 0) < 0.02
+
+
+def test_full_size_properties():
+    """BASELINE size (180 s, N=2048): masks sum to one, so the four stems add up to the
+    reconstructed mixture wherever a patch covers the frame; the tail is zero; repeatable."""
+    N = 2048
+    params, sep = make_sep(N, seed=0)
+    g = torch.Generator(device="cuda").manual_seed(9)
+    x = (torch.rand(7938000, generator=g, device="cuda") - 0.5) * 0.4
+    y = sep.separate_device(x)
+    torch.cuda.synchronize()
+    assert y.shape == (4, 7938000) and bool(torch.isfinite(y).all())
+    T = dsp.num_frames(7938000, 512)
+    P = patch.num_patches(T, 30, 25)
+    covered = ((P - 1) * 5 + 30 - 4) * 512 - N          # samples whose every frame has a mask
+    tot = y.sum(0)[:covered]
+    err = (torch.linalg.vector_norm(tot - x[:covered]) / torch.linalg.vector_norm(x[:covered])).item()
+    assert err < 1e-5, err
+    y2 = sep.separate_device(x)
+    assert torch.equal(y, y2)                             # deterministic (no atomics)
