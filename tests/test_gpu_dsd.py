@@ -67,6 +67,24 @@ def test_spec_level_matches_oracle():
     want = (mm[:, :T] / 0.3) * np.sqrt(N) * np.exp(1j * ph)[None]
     for s in range(4):
         assert rel(S[s], want[s]) <= TOL, (s, rel(S[s], want[s]))
+    # mask level, bin by bin.  The reference's mask is discontinuous where the rectified
+    # outputs of all sources vanish (1/4 each vs p/sum(p)): a bin whose float64 sum(p) is
+    # within fp32 noise of that kink cannot be reproduced by ANY fp32 evaluation.  Flag those
+    # with the oracle and require tight agreement everywhere else.
+    b, n = patch.generate_overlapadd(mag, F, 30, 25, 32)
+    pred = np.concatenate([nets.predict(params, bb, "dsd") for bb in b])[:n]   # [P,4,30,F]
+    near_kink = np.zeros((T, F), bool)
+    for k in range(n):
+        tot = pred[k].sum(axis=0)
+        near_kink[k * 5:k * 5 + 30] |= (tot < 1e-6) & (np.abs(pred[k]).max(axis=0) < 1e-6) & ~((tot == 0) & (pred[k].max(axis=0) == 0)) | ((tot > 0) & (tot < 1e-7))
+    Xn = np.abs(X)
+    ok = (Xn > 1e-3 * Xn.mean()) & ~near_kink
+    mg = np.abs(S) / np.maximum(Xn, 1e-30)
+    mw = np.abs(want) / np.maximum(Xn, 1e-30)
+    dm = np.abs(mg - mw)[:, ok]
+    assert near_kink.mean() < 1e-3
+    assert dm.max() < 2e-4, dm.max()
+    assert np.sqrt((dm ** 2).mean()) < 2e-6
     # frames past the last patch are exactly zero (stand-alone patcher drops the tail)
     P = patch.num_patches(T, 30, 25)
     assert sep.num_patches(T) == P

@@ -48,7 +48,12 @@ def test_golden_stft_istft(ctx, golden):
             S[0, :, :F] = torch.tensor(spec.astype(np.complex64), device="cuda")
             y = st.inverse(S).cpu().numpy()[0].astype(np.float64)
             assert y.shape == want.shape
-            assert rel(y, want) < 5e-6, (ci, rel(y, want))
+            # the last N/2 samples divide by sum(w^2) -> 0 (only the vanishing tail of the last
+            # frame covers them): ill-conditioned in any precision and cut by data[:L] in the
+            # pipeline.  Strict on the samples the pipeline keeps, loose on the full length.
+            keep = x.size
+            assert rel(y[:keep], want[:keep]) < 5e-6, (ci, rel(y[:keep], want[:keep]))
+            assert rel(y, want) < 1e-4, (ci, rel(y, want))
         # GPU round trip reconstructs the signal
         y = st.inverse(X.unsqueeze(0), num_out=x.size).cpu().numpy()[0]
         assert rel(y.astype(np.float64), x) < 5e-6
@@ -78,7 +83,8 @@ def test_polar_compute_file_and_inverse(ctx, N, H, wname):
     pt[:, :F] = torch.tensor(ph_r, dtype=torch.float32, device="cuda")
     y = st.inverse_polar(mt, pt).cpu().numpy().astype(np.float64)
     assert y.shape == y_r.shape
-    assert rel(y, y_r) < 5e-6
+    assert rel(y[:x.size], y_r[:x.size]) < 5e-6
+    assert rel(y, y_r) < 1e-4          # includes the ill-conditioned tail (sum(w^2) -> 0)
 
 
 def test_large_roundtrip_property(ctx):
