@@ -3,6 +3,7 @@
 #include <stdarg.h>
 #include <math.h>
 #include <string.h>
+#include <stdlib.h>
 #include <vector>
 #include "common.cuh"
 
@@ -70,6 +71,8 @@ struct dcs_model {
   int64_t ldw;
   std::vector<float*> dev;  // owned device arrays
   float *W1f, *b1, *W2c, *b2, *Wfc, *bfc, *Wdec, *bdec, *Wt2, *W1t, *bout;
+  // tensor-core copies of the GEMM weights (K-major, 3xTF32 split)
+  dcs::TcWeight tW1f, tW2c, tWfc, tWdec, tWt2;
 };
 
 extern "C" {
@@ -95,6 +98,10 @@ int dcs_create(int device, dcs_ctx** out) {
   dcs_ctx* c = new dcs_ctx();
   c->device = device;
   c->num_sms = prop.multiProcessorCount;
+  const char* dbg = getenv("DCS_DEBUG_SIMT_GEMM");
+  c->debug_simt_gemm = dbg && dbg[0] == '1';
+  const char* am = getenv("DCS_DEBUG_TC_ACC");
+  if (am && am[0] >= '0' && am[0] <= '2') c->tc_acc_mode = am[0] - '0';
   *out = c;
   return DCS_OK;
 }
@@ -221,6 +228,8 @@ int dcs_model_nsources(const dcs_model* m) { return m ? m->nsrc : 0; }
 int dcs_model_destroy(dcs_model* m) {
   if (!m) return DCS_OK;
   for (float* d : m->dev) cudaFree(d);
+  tc_weight_destroy(&m->tW1f); tc_weight_destroy(&m->tW2c); tc_weight_destroy(&m->tWfc);
+  tc_weight_destroy(&m->tWdec); tc_weight_destroy(&m->tWt2);
   delete m;
   return DCS_OK;
 }
@@ -284,6 +293,11 @@ static int model_create_dsd(dcs_model* m, int nparams, const float* const* hp, c
     DCS_TRY(upload(*u.h, u.d));
     m->dev.push_back(*u.d);
   }
+  DCS_TRY(tc_weight_create(W1f.data(), C1, F, C1, &m->tW1f));
+  DCS_TRY(tc_weight_create(W2c.data(), C2, kh2 * C1, C2, &m->tW2c));
+  DCS_TRY(tc_weight_create(Wfcp.data(), nfc, flat, nfc, &m->tWfc));
+  DCS_TRY(tc_weight_create(Wdec.data(), ndec * flat, nfc, ndec * flat, &m->tWdec));
+  DCS_TRY(tc_weight_create(Wt2.data(), C1, kh2 * C2, C1, &m->tWt2));
   return DCS_OK;
 }
 
@@ -308,6 +322,12 @@ int dcs_model_create(dcs_ctx* ctx, int arch, int feat_size, int time_context, in
 }
 
 // ------------------------------------------------------------------------------------ pipeline
+// every dense contraction goes to the tcgen05 kernel; DCS_DEBUG_SIMT_GEMM=1 (read once in
+// dcs_create) routes them to the FFMA kernel instead -- a bring-up aid, not a fallback.
+static int run_gemm(dcs_ctx* ctx, const GemmDesc& d, const TcWeight& w, cudaStream_t st) {
+  return ctx->debug_simt_gemm ? launch_gemm(ctx, d, st) : launch_gemm_tc(ctx, d, w, st);
+}
+
 static int dsd_forward(dcs_ctx* ctx, dcs_model* m, const float* d_mag, const float2* d_X, int64_t T, int64_t ldf,
                        int overlap, int patcher, float2* d_S, int64_t src_stride, cudaStream_t st) {
   const int tc = m->tc, step = tc - overlap, C1 = m->C1, C2 = m->C2, kh2 = m->kh2, h2 = m->h2, nfc = m->nfc;
@@ -330,27 +350,29 @@ static int dsd_forward(dcs_ctx* ctx, dcs_model* m, const float* d_mag, const flo
   // conv1 + both biases, once per frame (kernel height 1): H1[Tp][C1] = mag[T][F] * W1f
   GemmDesc g1 = gemm_plain(d_mag, ldf, m->W1f, C1, m->b1, H1, C1, (int)Tp, C1, m->F, 0);
   g1.a_valid_rows = (int)T;  // util patcher: frames beyond T are zero input
-  { ProfScope ps(ctx, "enc_conv1_gemm", st); DCS_TRY(launch_gemm(ctx, g1, st)); }
+  { ProfScope ps(ctx, "enc_conv1_gemm", st); DCS_TRY(run_gemm(ctx, g1, m->tW1f, st)); }
   // conv2 + both biases, once per frame offset: rows overlap in H1 (stride C1, length kh2*C1)
   GemmDesc g2 = gemm_plain(H1, C1, m->W2c, C2, m->b2, H2, C2, (int)(Tp - kh2 + 1), C2, kh2 * C1, 0);
-  { ProfScope ps(ctx, "enc_conv2_gemm", st); DCS_TRY(launch_gemm(ctx, g2, st)); }
+  { ProfScope ps(ctx, "enc_conv2_gemm", st); DCS_TRY(run_gemm(ctx, g2, m->tW2c, st)); }
   // bottleneck: patch k reads H2 rows k*step .. k*step+h2-1 (contiguous h2*C2 floats)
   GemmDesc g3 = gemm_plain(H2, (int64_t)step * C2, m->Wfc, nfc, m->bfc, z, nfc, (int)P, nfc, h2 * C2, 1);
-  { ProfScope ps(ctx, "bottleneck_gemm", st); DCS_TRY(launch_gemm(ctx, g3, st)); }
+  { ProfScope ps(ctx, "bottleneck_gemm", st); DCS_TRY(run_gemm(ctx, g3, m->tWfc, st)); }
   // three decoder dense layers side by side, scattered into the zero-padded buffer
   GemmDesc g4 = gemm_plain(z, nfc, m->Wdec, 3 * h2 * C2, m->bdec, ap, (int64_t)3 * HP * C2, (int)P, 3 * h2 * C2, nfc, 1);
   g4.n_seg = h2 * C2; g4.n_ss = (int64_t)HP * C2; g4.c_col0 = (int64_t)(kh2 - 1) * C2;
-  { ProfScope ps(ctx, "dec_dense_gemm", st); DCS_TRY(launch_gemm(ctx, g4, st)); }
+  { ProfScope ps(ctx, "dec_dense_gemm", st); DCS_TRY(run_gemm(ctx, g4, m->tWdec, st)); }
   // InverseLayer(conv2): full correlation on the padded activations, rows (k, d, u)
   GemmDesc g5 = gemm_plain(ap, 0, m->Wt2, C1, nullptr, G, ldg, (int)(P * 3 * tc), C1, kh2 * C2, 0);
   g5.m_inner = tc; g5.a_so = (int64_t)HP * C2; g5.a_si = C2;
-  { ProfScope ps(ctx, "dec_convT2_gemm", st); DCS_TRY(launch_gemm(ctx, g5, st)); }
+  { ProfScope ps(ctx, "dec_convT2_gemm", st); DCS_TRY(run_gemm(ctx, g5, m->tWt2, st)); }
   // InverseLayer(conv1) + bias + ReLU + mask + cross-fade + phase
   DsdMaskArgs a;
   a.G = G; a.ldg = ldg; a.W1t = m->W1t; a.ldw = (int)m->ldw; a.bout = m->bout; a.X = d_X; a.S = d_S;
   a.ldf = ldf; a.src_stride = src_stride; a.T = (int)T; a.P = (int)P; a.tc = tc; a.overlap = overlap; a.F = m->F;
+  a.only_nyquist = 0;
   ProfScope ps(ctx, "dec_convT1_mask_xfade", st);
-  return launch_dsd_mask(ctx, a, st);
+  if (!ctx->debug_simt_gemm && dsd_mask_tc_supported(a)) return launch_dsd_mask_tc(ctx, a, st);
+  return launch_dsd_mask(ctx, a, st);   // FFMA kernel: > 6 patches per frame, or bring-up cross-check
 }
 
 int dcs_separate_spec(dcs_ctx* ctx, dcs_model* m, const float* d_mag, const dcs_complex* d_X, int64_t T, int64_t ldf,
@@ -366,6 +388,44 @@ int dcs_separate_spec(dcs_ctx* ctx, dcs_model* m, const float* d_mag, const dcs_
                          (cudaStream_t)stream);
   }
   DCS_REQUIRE(false, "architecture %d has no CUDA path yet", m->arch);
+}
+
+int dcs_gemm_f32(dcs_ctx* ctx, int engine, const float* d_A, int64_t lda, const float* h_B, int64_t ldb,
+                 const float* h_bias, float* d_C, int64_t ldc, int M, int N, int K, int relu, void* stream) {
+  DCS_REQUIRE(ctx && d_A && h_B && d_C && M > 0 && N > 0 && K > 0, "dcs_gemm_f32: bad argument");
+  DCS_REQUIRE(lda >= 1 && ldb >= N && ldc >= N, "dcs_gemm_f32: leading dimension too small");  // lda < K: overlapping rows
+  cudaStream_t st = (cudaStream_t)stream;
+  DCS_CUDA(cudaSetDevice(ctx->device));
+  float* d_bias = nullptr;
+  float* d_B = nullptr;
+  TcWeight w;
+  int r = DCS_OK;
+  if (h_bias) {
+    std::vector<float> hb(h_bias, h_bias + N);
+    r = upload(hb, &d_bias);
+  }
+  GemmDesc g = gemm_plain(d_A, lda, nullptr, N, d_bias, d_C, ldc, M, N, K, relu);
+  if (r == DCS_OK) {
+    if (engine == 1) {
+      r = tc_weight_create(h_B, ldb, K, N, &w);
+      if (r == DCS_OK) r = launch_gemm_tc(ctx, g, w, st);
+    } else {
+      std::vector<float> hB((size_t)K * N);
+      for (int k = 0; k < K; ++k) memcpy(&hB[(size_t)k * N], h_B + (size_t)k * ldb, (size_t)N * sizeof(float));
+      r = upload(hB, &d_B);
+      g.B = d_B;
+      if (r == DCS_OK) r = launch_gemm(ctx, g, st);
+    }
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  tc_weight_destroy(&w);
+  if (d_B) cudaFree(d_B);
+  if (d_bias) cudaFree(d_bias);
+  if (r == DCS_OK && e != cudaSuccess) {
+    set_error("dcs_gemm_f32: %s", cudaGetErrorString(e));
+    return DCS_ECUDA;
+  }
+  return r;
 }
 
 int dcs_separate_audio(dcs_ctx* ctx, dcs_model* m, dcs_stft* p, const float* d_audio, int64_t L, float scale_factor,

@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string>
 #include <vector>
+#include <string.h>
 #include "../../include/dcs.h"
 
 namespace dcs {
@@ -59,6 +60,8 @@ struct dcs_ctx {
   int num_sms = 148;
   int64_t launches = 0;
   bool prof_on = false;
+  bool debug_simt_gemm = false;
+  int tc_acc_mode = 2;
   std::vector<dcs_prof_rec> prof;
   // workspace of one in-flight pipeline
   dcs::DevBuf audio, X, mag, S, stems, pcm_in, pcm_out;
@@ -116,6 +119,16 @@ GemmDesc gemm_plain(const float* A, int64_t lda, const float* B, int64_t ldb, co
                     int64_t ldc, int M, int N, int K, int relu);
 int launch_gemm(dcs_ctx* ctx, const GemmDesc& d, cudaStream_t st);
 
+// weight matrix prepared for the tensor-core path: K-major, zero padded, split for 3xTF32
+struct TcWeight {
+  float* hi = nullptr;
+  float* lo = nullptr;
+  int K = 0, N = 0, Kp = 0, Np = 0;
+};
+int tc_weight_create(const float* B_rowmajor, int64_t ldb, int K, int N, TcWeight* out);
+void tc_weight_destroy(TcWeight* w);
+int launch_gemm_tc(dcs_ctx* ctx, const GemmDesc& d, const TcWeight& w, cudaStream_t st);
+
 struct DsdMaskArgs {
   const float* G;      // [P][3][tc][ldg]  decoder activations after the transposed conv2
   int ldg;
@@ -126,8 +139,11 @@ struct DsdMaskArgs {
   float2* S;           // [4][T][ldf]
   int64_t ldf, src_stride;
   int T, P, tc, overlap, F;
+  int only_nyquist;    // FFMA kernel: compute bin F-1 only (the tensor-core kernel did the rest)
 };
 int launch_dsd_mask(dcs_ctx* ctx, const DsdMaskArgs& a, cudaStream_t st);
+bool dsd_mask_tc_supported(const DsdMaskArgs& a);
+int launch_dsd_mask_tc(dcs_ctx* ctx, const DsdMaskArgs& a, cudaStream_t st);
 
 int launch_pcm_decode(dcs_ctx* ctx, const int16_t* d_pcm, int64_t L, int channels, int downmix, float* d_audio,
                       cudaStream_t st);

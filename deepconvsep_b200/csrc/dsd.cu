@@ -31,7 +31,7 @@ dsd_mask_kernel(const DsdMaskArgs a, int frames_per_cta) {
   int b = -1;
   if (tid < MASK_TILE) {
     const int bb = blockIdx.x * MASK_TILE + tid;
-    if (bb < a.F - 1) b = bb;
+    if (bb < a.F - 1 && !a.only_nyquist) b = bb;
   } else if (tid == MASK_TILE && blockIdx.x == 0) {
     b = a.F - 1;
   }
@@ -121,7 +121,7 @@ int launch_dsd_mask(dcs_ctx* ctx, const DsdMaskArgs& a, cudaStream_t st) {
   if (a.T <= 0) return DCS_OK;
   DCS_REQUIRE(a.tc > a.overlap && a.overlap >= 0, "time_context %d must exceed overlap %d", a.tc, a.overlap);
   const int fpc = 16;
-  dim3 grid((unsigned)ceil_div64(a.F - 1, MASK_TILE), (unsigned)ceil_div64(a.T, fpc));
+  dim3 grid(a.only_nyquist ? 1u : (unsigned)ceil_div64(a.F - 1, MASK_TILE), (unsigned)ceil_div64(a.T, fpc));
   dsd_mask_kernel<50><<<grid, MASK_THREADS, 0, st>>>(a, fpc);
   DCS_CHECK_LAUNCH();
   ctx->launches++;

@@ -1,0 +1,157 @@
+// tc.cuh -- inline-PTX wrappers for the Blackwell (sm_100a) tensor-core path: tcgen05.mma
+// (kind::tf32) with accumulators in TMEM, mbarrier pipelines, shared-memory matrix descriptors.
+//
+// Operand layout used everywhere in this library: K-major, SWIZZLE_128B.  A tile of R rows x 32
+// fp32 (one pipeline stage, K = 32 = one 128-byte swizzle atom) is stored row by row, 128 bytes
+// per row, rows grouped by 8 (1024 bytes, SBO); inside a group the 16-byte chunk index is XORed
+// with the row index (cute Swizzle<3,4,3>):
+//     byte_offset(r, k) = (r / 8) * 1024 + (r % 8) * 128 + (((k / 4) ^ (r % 8)) * 16) + (k % 4) * 4
+// Tile bases must be 1024-byte aligned.  One tcgen05.mma of kind::tf32 consumes K = 8 (32 bytes):
+// k-step j of a stage starts 32*j bytes into the tile (the hardware applies the XOR on the
+// absolute address).  (The un-swizzled "interleave" layout is functionally fine but its operand
+// fetch runs at 16 B/clk: measured 10x slower MMAs -- profiles/r1_notes.md.)
+//
+// fp32 accuracy on the tf32 pipe ("3xTF32"): x = hi + lo with hi = x truncated to tf32 (low 13
+// mantissa bits cleared) and lo = x - hi (exact); D += Ahi*Bhi + Alo*Bhi + Ahi*Blo.  The dropped
+// Alo*Blo term is ~2^-20 relative.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dcs {
+namespace tc {
+
+constexpr int KSTAGE = 32;                 // fp32 elements of K per pipeline stage
+constexpr int ROW_BYTES = KSTAGE * 4;      // 128 bytes per row per stage
+constexpr uint32_t SBO = 1024;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier -------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "DCS_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DCS_DONE;\n\t"
+      "bra DCS_WAIT;\n\t"
+      "DCS_DONE:\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma operand reads)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- TMEM -----------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {  // whole warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  // whole warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// 16 consecutive fp32 columns of this warp's 32 TMEM lanes (thread = lane)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// same loads without the wait: issue several, then tmem_wait_ld() once
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld2_nowait(uint32_t taddr, float* v) {
+  uint32_t r0, r1;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(taddr));
+  v[0] = __uint_as_float(r0);
+  v[1] = __uint_as_float(r1);
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, float (&v)[2]) {
+  uint32_t r0, r1;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  v[0] = __uint_as_float(r0);
+  v[1] = __uint_as_float(r1);
+}
+
+// ---- descriptors ----------------------------------------------------------------------------
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30)
+// (ignored for swizzled K-major; 1 as CUTLASS encodes it), SBO>>4 [32,46), version=1 [46,48),
+// base_offset=0 (1024-aligned tiles), layout_type=2 (SWIZZLE_128B) [61,64)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(SBO >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+constexpr uint32_t KSTEP_BYTES = 32;  // descriptor start-address advance per k-step (8 tf32)
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), both
+// K-major, N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T, issued by ONE thread
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on `bar` when every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---- 3xTF32 operand split ---------------------------------------------------------------------
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  lo = x - hi;
+}
+__device__ __forceinline__ void split4(const float4 x, float4& hi, float4& lo) {
+  split_tf32(x.x, hi.x, lo.x);
+  split_tf32(x.y, hi.y, lo.y);
+  split_tf32(x.z, hi.z, lo.z);
+  split_tf32(x.w, hi.w, lo.w);
+}
+// byte offset of (row r, 16-byte chunk c) inside one stage tile (128B swizzle)
+__device__ __forceinline__ uint32_t tile_off(int r, int c) {
+  return (uint32_t)((r >> 3) * SBO + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+}
+// 1024-byte aligned start of the dynamic shared memory window
+__device__ __forceinline__ uint8_t* align1024(uint8_t* p) {
+  const uint32_t a = smem_u32(p);
+  return p + (((a + 1023u) & ~1023u) - a);
+}
+
+}  // namespace tc
+}  // namespace dcs

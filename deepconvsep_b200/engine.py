@@ -73,6 +73,19 @@ class Context(object):
         nm = names.value.decode().split("\n")[:n]
         return list(zip(nm, [float(ms[i]) for i in range(n)]))
 
+    def gemm(self, A, B, bias=None, relu=False, engine=1, stream=None):
+        """torch float32 cuda A [M,K] (row stride A.stride(0)) x numpy B [K,N] -> torch [M,N]."""
+        import torch
+        M, K = A.shape
+        Bh = np.ascontiguousarray(B, dtype=np.float32)
+        N = Bh.shape[1]
+        bh = None if bias is None else np.ascontiguousarray(bias, dtype=np.float32)
+        Cd = torch.empty((M, N), dtype=torch.float32, device=A.device)
+        _lib.check(self.lib.dcs_gemm_f32(self.handle, int(engine), _ptr(A), A.stride(0), Bh.ctypes.data, N,
+                                         None if bh is None else bh.ctypes.data, _ptr(Cd), N, M, N, K, int(relu),
+                                         _stream_ptr(stream)))
+        return Cd
+
     def close(self):
         if getattr(self, "handle", None):
             self.lib.dcs_destroy(self.handle)

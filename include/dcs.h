@@ -128,6 +128,15 @@ int dcs_separate_spec(dcs_ctx* ctx, dcs_model* model, const float* d_mag, const 
                       int64_t num_frames, int64_t ldf, int overlap, int patcher, dcs_complex* d_S,
                       int64_t src_stride, void* stream);
 
+/* ---- building block: the dense layer / im2col-free convolution GEMM ------------------------ */
+/* d_C[M][ldc] = act(d_A[M][lda] * h_B[K][ldb] (+ h_bias[N])), fp32 in / fp32 out.  The weight is a
+ * HOST array (it is transposed, padded and split for the tensor cores on the fly -- the models
+ * do that once at load time).  engine 1: tcgen05 kind::tf32 with the 3xTF32 split (the product
+ * path); engine 0: exact-fp32 FFMA kernel (bring-up cross-check).  lasagne DenseLayer
+ * (separate_dsd.py:206-221) is this with relu=1.  Synchronises the stream before returning. */
+int dcs_gemm_f32(dcs_ctx* ctx, int engine, const float* d_A, int64_t lda, const float* h_B, int64_t ldb,
+                 const float* h_bias, float* d_C, int64_t ldc, int M, int N, int K, int relu, void* stream);
+
 /* ---- whole train_auto() on device buffers (separate_dsd.py:289-306) ----------------------- */
 /* d_audio float[L] mono in [-1,1] -> d_stems float[nsrc][stem_stride] (first L samples valid) */
 int dcs_separate_audio(dcs_ctx* ctx, dcs_model* model, dcs_stft* plan, const float* d_audio,
