@@ -100,6 +100,8 @@ int dcs_create(int device, dcs_ctx** out) {
   c->num_sms = prop.multiProcessorCount;
   const char* dbg = getenv("DCS_DEBUG_SIMT_GEMM");
   c->debug_simt_gemm = dbg && dbg[0] == '1';
+  const char* sf = getenv("DCS_DEBUG_SMEM_FFT");
+  c->debug_smem_fft = sf && sf[0] == '1';
   const char* am = getenv("DCS_DEBUG_TC_ACC");
   if (am && am[0] >= '0' && am[0] <= '2') c->tc_acc_mode = am[0] - '0';
   *out = c;

@@ -62,6 +62,7 @@ struct dcs_ctx {
   bool prof_on = false;
   bool debug_simt_gemm = false;
   int tc_acc_mode = 2;
+  bool debug_smem_fft = false;
   std::vector<dcs_prof_rec> prof;
   // workspace of one in-flight pipeline
   dcs::DevBuf audio, X, mag, S, stems, pcm_in, pcm_out;
@@ -102,6 +103,13 @@ int launch_stft(dcs_stft* plan, const float* d_audio, int64_t L, float2* d_X, fl
 int launch_istft(dcs_stft* plan, const float2* d_S, const float* d_mag, const float* d_phase,
                  float polar_scale, int nsrc, int64_t T, int64_t ldf, int64_t src_stride, float* d_out,
                  int64_t Lout, int64_t out_stride, cudaStream_t st);
+
+bool stft_reg_supported(int N);
+int launch_stft_reg(dcs_stft* plan, const float* d_audio, int64_t L, float2* d_X, float* d_mag, float* d_phase,
+                    float mag_scale, int64_t ldf, int64_t nframes, cudaStream_t st);
+bool istft_reg_supported(const dcs_stft* plan, const float* d_out, int64_t out_stride);
+int launch_istft_reg(dcs_stft* plan, const float2* d_S, int nsrc, int64_t nframes, int64_t ldf, int64_t src_stride,
+                     float* d_out, int64_t Lout, int64_t out_stride, cudaStream_t st);
 
 // generic strided-operand GEMM  C = act(A*B + bias)
 struct GemmDesc {

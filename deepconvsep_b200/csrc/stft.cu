@@ -191,7 +191,9 @@ int launch_stft(dcs_stft* p, const float* d_audio, int64_t L, float2* d_X, float
                 float mag_scale, int64_t ldf, cudaStream_t st) {
   const int64_t T = dcs_num_frames(L, p->hop);
   DCS_REQUIRE(ldf >= p->N / 2 + 1, "ldf %lld < F %d", (long long)ldf, p->N / 2 + 1);
-  DCS_REQUIRE(ldf - (p->N / 2 + 1) <= p->N / 8, "ldf %lld pads more than %d columns", (long long)ldf, p->N / 8);
+  DCS_REQUIRE(ldf - (p->N / 2 + 1) <= 16, "ldf %lld pads more than 16 columns", (long long)ldf);
+  if (stft_reg_supported(p->N) && !p->ctx->debug_smem_fft)
+    return launch_stft_reg(p, d_audio, L, d_X, d_mag, d_phase, mag_scale, ldf, T, st);
   switch (p->N) {
     case 256: return launch_stft_n<256>(p, d_audio, L, d_X, d_mag, d_phase, mag_scale, ldf, T, st);
     case 512: return launch_stft_n<512>(p, d_audio, L, d_X, d_mag, d_phase, mag_scale, ldf, T, st);
@@ -230,6 +232,8 @@ int launch_istft(dcs_stft* p, const float2* d_S, const float* d_mag, const float
                  int64_t out_stride, cudaStream_t st) {
   DCS_REQUIRE(Lout <= (T - 1) * p->hop + p->N - p->N / 2, "num_out %lld exceeds the istft length", (long long)Lout);
   if (Lout <= 0 || nsrc <= 0) return DCS_OK;
+  if (d_S && istft_reg_supported(p, d_out, out_stride) && !p->ctx->debug_smem_fft)
+    return launch_istft_reg(p, d_S, nsrc, T, ldf, src_stride, d_out, Lout, out_stride, st);
 #define DCS_ISTFT_CASE(NN) \
   case NN: return launch_istft_n<NN>(p, d_S, d_mag, d_phase, polar_scale, nsrc, T, ldf, src_stride, d_out, Lout, out_stride, st);
   switch (p->N) {

@@ -1,0 +1,233 @@
+// stft_reg.cu -- STFT (K1) and iSTFT + overlap-add (K4) with the register-resident FFT of
+// fft_reg.cuh, for frame sizes 1024 and 2048 (the DSD100 / iKala configurations).  Same reference
+// semantics as stft.cu (transform.py:277-396); that file's shared-memory Stockham kernels remain
+// the path for the other frame sizes / hops.
+//
+// K1: one group of T = N/64 threads (a warp for N = 2048) owns a frame: hop-overlapped, windowed
+//     samples go from global memory straight into registers, the spectrum is staged once in the
+//     group's scratch so that the real-FFT split and the X / mag rows leave fully coalesced.
+// K4: a group owns `hops_per_group` consecutive output hops of one source and walks the frames
+//     that overlap them IN FRAME ORDER, keeping the overlap-add window (N samples) in registers:
+//     after frame n is added, the oldest hop is complete -> divided by sum(win*syn_win), stored
+//     coalesced, and the window shifts.  No shared accumulator, no atomics: the summation order
+//     is the reference's (ascending frame index) and the result is run-to-run deterministic.
+//     N/hop - 1 halo frames are recomputed at the start of each span.
+#include "common.cuh"
+#include "fft_reg.cuh"
+
+namespace dcs {
+
+constexpr int REG_THREADS = 128;
+
+template <int T>
+__global__ void __launch_bounds__(REG_THREADS)
+stft_reg_kernel(const float* __restrict__ audio, int64_t L, int hop, const float* __restrict__ win,
+                const float2* __restrict__ tw, float2* __restrict__ X, float* __restrict__ mag,
+                float* __restrict__ phase, int64_t ldf, int64_t nframes, float mag_scale, int frames_per_group) {
+  using G = FftGroup<T>;
+  constexpr int N2 = G::N2, N = 2 * N2, F = N2 + 1, GPC = REG_THREADS / T;
+  extern __shared__ __align__(16) float2 scratch[];
+  const int tid = threadIdx.x, b = tid % T, gl = tid / T;
+  float2* scr = scratch + gl * G::SCRATCH;
+  const int64_t g = (int64_t)blockIdx.x * GPC + gl;
+  const int64_t warp_first = ((int64_t)blockIdx.x * GPC + (tid / 32) * (32 / T)) * frames_per_group;
+  for (int i = 0; i < frames_per_group; ++i) {
+    if (warp_first + i >= nframes) break;  // warp-uniform: even the warp's first group is past the end
+    const int64_t n = g * frames_per_group + i;
+    const bool valid = n < nframes;
+    const int64_t base = n * hop - N / 2;
+    float2 v[32];
+#pragma unroll
+    for (int a = 0; a < 32; ++a) {
+      const int idx = a * T + b;
+      const int64_t s = base + 2 * idx;
+      const float2 w = __ldg(reinterpret_cast<const float2*>(win) + idx);
+      const float x0 = (valid && s >= 0 && s < L) ? __ldg(audio + s) : 0.f;
+      const float x1 = (valid && s + 1 >= 0 && s + 1 < L) ? __ldg(audio + s + 1) : 0.f;
+      v[a] = make_float2(x0 * w.x, x1 * w.y);
+    }
+    G::forward(v, scr, tw, b);
+#pragma unroll
+    for (int q = 0; q < G::Q; ++q)
+#pragma unroll
+      for (int kb = 0; kb < T; ++kb) scr[(b + T * q) + 32 * kb] = v[q * T + kb];
+    __syncwarp();
+    if (valid) {
+      const int64_t row = n * ldf;
+#pragma unroll 4
+      for (int m = 0; m < N2 / T; ++m) {
+        const int k = b + T * m;
+        const float2 xk = real_post<N2>(scr, tw, k);
+        if (X) X[row + k] = xk;
+        if (mag) mag[row + k] = mag_scale * sqrtf(xk.x * xk.x + xk.y * xk.y);
+        if (phase) phase[row + k] = atan2f(xk.y, xk.x);
+      }
+      if (b == 0) {  // Nyquist bin
+        const float2 z0 = scr[0];
+        const float vv = z0.x - z0.y;
+        if (X) X[row + N2] = make_float2(vv, 0.f);
+        if (mag) mag[row + N2] = mag_scale * fabsf(vv);
+        if (phase) phase[row + N2] = atan2f(0.f, vv);
+      }
+      if (b < ldf - F) {  // pad columns
+        if (X) X[row + F + b] = make_float2(0.f, 0.f);
+        if (mag) mag[row + F + b] = 0.f;
+        if (phase) phase[row + F + b] = 0.f;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <int T, int HS>  // HS = hop / 64: window slots (32 float2 each) per hop
+__global__ void __launch_bounds__(REG_THREADS)
+istft_reg_kernel(const float2* __restrict__ S, int64_t nframes, int64_t ldf, int64_t src_stride,
+                 const float* __restrict__ wsyn, const float* __restrict__ w2, const float2* __restrict__ tw,
+                 float* __restrict__ out, int64_t Lout, int64_t out_stride, int hops_per_group, int64_t num_hops,
+                 int64_t groups_per_src, int64_t total_groups) {
+  using G = FftGroup<T>;
+  constexpr int N2 = G::N2, N = 2 * N2, hop = 64 * HS, R = N / hop, C0 = (N / 2) / hop, GPC = REG_THREADS / T;
+  extern __shared__ __align__(16) float2 scratch[];
+  const int tid = threadIdx.x, b = tid % T, gl = tid / T;
+  float2* scr = scratch + gl * G::SCRATCH;
+  int64_t gi = (int64_t)blockIdx.x * GPC + gl;
+  const bool active = gi < total_groups;
+  if (!active) gi = total_groups - 1;  // keeps the warp convergent; nothing is stored
+  const int src = (int)(gi / groups_per_src);
+  const int64_t h0 = (gi % groups_per_src) * hops_per_group;
+  const float inv_n2 = 1.0f / (float)N2;
+  float2 acc[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) acc[i] = make_float2(0.f, 0.f);
+  float* o = out + (int64_t)src * out_stride;
+
+  for (int64_t n = h0 + C0 - R + 1; n <= h0 + hops_per_group - 1 + C0; ++n) {
+    const bool fvalid = n >= 0 && n < nframes;
+    const int64_t row = (int64_t)src * src_stride + (fvalid ? n : 0) * ldf;
+    float2 v[32];
+#pragma unroll
+    for (int a = 0; a < 32; ++a) {
+      const int idx = a * T + b;
+      float2 xk = make_float2(0.f, 0.f), xn = xk;
+      if (fvalid) {
+        xk = S[row + idx];
+        xn = S[row + N2 - idx];
+      }
+      if (idx == 0) { xk.y = 0.f; xn.y = 0.f; }  // irfft ignores Im of DC and Nyquist
+      v[a] = real_pre_conj(xk, xn, __ldg(tw + idx));
+    }
+    G::forward(v, scr, tw, b);
+    // z = conj(V)/N2: samples 2n', 2n'+1 of the frame, n' = (b + T q) + 32 kb  <->  v[q*T + kb]
+#pragma unroll
+    for (int q = 0; q < G::Q; ++q)
+#pragma unroll
+      for (int kb = 0; kb < T; ++kb) {
+        const int np = (b + T * q) + 32 * kb;
+        const float2 w = __ldg(reinterpret_cast<const float2*>(wsyn) + np);
+        const float2 r = v[q * T + kb];
+        acc[q * T + kb].x = fmaf(w.x, r.x * inv_n2, acc[q * T + kb].x);
+        acc[q * T + kb].y = fmaf(w.y, -r.y * inv_n2, acc[q * T + kb].y);
+      }
+    // the oldest hop of the window is complete: padded samples [n*hop, (n+1)*hop) -> output hop n - C0
+    const int64_t h = n - C0;
+    if (active && h >= h0 && h < num_hops) {
+#pragma unroll
+      for (int q = 0; q < G::Q; ++q)
+#pragma unroll
+        for (int kb = 0; kb < HS; ++kb) {
+          const int e = 2 * ((b + T * q) + 32 * kb);  // sample offset inside the hop
+          float c0 = 0.f, c1 = 0.f;                   // sum of win*syn_win over the frames covering it
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const int64_t nf = n - r;
+            if (nf >= 0 && nf < nframes) {
+              const float2 ww = __ldg(reinterpret_cast<const float2*>(w2 + e + r * hop));
+              c0 += ww.x;
+              c1 += ww.y;
+            }
+          }
+          if (c0 == 0.f) c0 = 1.f;  // transform.py:392
+          if (c1 == 0.f) c1 = 1.f;
+          const int64_t oi = h * hop + e;
+          const float2 a2 = acc[q * T + kb];
+          if (oi + 1 < Lout) {
+            *reinterpret_cast<float2*>(o + oi) = make_float2(a2.x / c0, a2.y / c1);
+          } else if (oi < Lout) {
+            o[oi] = a2.x / c0;
+          }
+        }
+    }
+    // shift the window by one hop
+#pragma unroll
+    for (int q = 0; q < G::Q; ++q) {
+#pragma unroll
+      for (int kb = 0; kb < T - HS; ++kb) acc[q * T + kb] = acc[q * T + kb + HS];
+#pragma unroll
+      for (int kb = T - HS; kb < T; ++kb) acc[q * T + kb] = make_float2(0.f, 0.f);
+    }
+  }
+}
+
+bool stft_reg_supported(int N) { return N == 1024 || N == 2048; }
+
+int launch_stft_reg(dcs_stft* p, const float* d_audio, int64_t L, float2* d_X, float* d_mag, float* d_phase,
+                    float mag_scale, int64_t ldf, int64_t nframes, cudaStream_t st) {
+  const int fpg = 4;
+  const float ms = mag_scale / sqrtf((float)p->N);
+  if (p->N == 2048) {
+    using G = FftGroup<32>;
+    const int gpc = REG_THREADS / 32;
+    const unsigned grid = (unsigned)ceil_div64(nframes, (int64_t)gpc * fpg);
+    stft_reg_kernel<32><<<grid, REG_THREADS, gpc * G::SCRATCH * sizeof(float2), st>>>(
+        d_audio, L, p->hop, p->d_win, p->d_tw, d_X, d_mag, d_phase, ldf, nframes, ms, fpg);
+  } else {
+    using G = FftGroup<16>;
+    const int gpc = REG_THREADS / 16;
+    const unsigned grid = (unsigned)ceil_div64(nframes, (int64_t)gpc * fpg);
+    stft_reg_kernel<16><<<grid, REG_THREADS, gpc * G::SCRATCH * sizeof(float2), st>>>(
+        d_audio, L, p->hop, p->d_win, p->d_tw, d_X, d_mag, d_phase, ldf, nframes, ms, fpg);
+  }
+  DCS_CHECK_LAUNCH();
+  p->ctx->launches++;
+  return DCS_OK;
+}
+
+bool istft_reg_supported(const dcs_stft* p, const float* d_out, int64_t out_stride) {
+  return (p->N == 1024 || p->N == 2048) && (p->hop == 512 || p->hop == 256) && ((uintptr_t)d_out % 8 == 0) &&
+         out_stride % 2 == 0;
+}
+
+template <int T, int HS>
+static int launch_istft_reg_t(dcs_stft* p, const float2* d_S, int nsrc, int64_t nframes, int64_t ldf, int64_t src_stride,
+                              float* d_out, int64_t Lout, int64_t out_stride, cudaStream_t st) {
+  using G = FftGroup<T>;
+  constexpr int GPC = REG_THREADS / T;
+  const int hop = 64 * HS;
+  const int64_t num_hops = ceil_div64(Lout, hop);
+  // hops per group: long enough to amortise the N/hop-1 halo frames, short enough to give every
+  // SM several waves of groups
+  const int64_t target_groups = (int64_t)p->ctx->num_sms * 12 * (32 / T) * 2;
+  int64_t hpg = ceil_div64((int64_t)nsrc * num_hops, target_groups);
+  if (hpg < 12) hpg = 12;
+  if (hpg > 64) hpg = 64;
+  const int64_t groups_per_src = ceil_div64(num_hops, hpg);
+  const int64_t total = groups_per_src * nsrc;
+  const unsigned grid = (unsigned)ceil_div64(total, GPC);
+  istft_reg_kernel<T, HS><<<grid, REG_THREADS, GPC * G::SCRATCH * sizeof(float2), st>>>(
+      d_S, nframes, ldf, src_stride, p->d_wsyn, p->d_w2, p->d_tw, d_out, Lout, out_stride, (int)hpg, num_hops,
+      groups_per_src, total);
+  DCS_CHECK_LAUNCH();
+  p->ctx->launches++;
+  return DCS_OK;
+}
+
+int launch_istft_reg(dcs_stft* p, const float2* d_S, int nsrc, int64_t nframes, int64_t ldf, int64_t src_stride,
+                     float* d_out, int64_t Lout, int64_t out_stride, cudaStream_t st) {
+  if (p->N == 2048 && p->hop == 512) return launch_istft_reg_t<32, 8>(p, d_S, nsrc, nframes, ldf, src_stride, d_out, Lout, out_stride, st);
+  if (p->N == 2048 && p->hop == 256) return launch_istft_reg_t<32, 4>(p, d_S, nsrc, nframes, ldf, src_stride, d_out, Lout, out_stride, st);
+  if (p->N == 1024 && p->hop == 512) return launch_istft_reg_t<16, 8>(p, d_S, nsrc, nframes, ldf, src_stride, d_out, Lout, out_stride, st);
+  if (p->N == 1024 && p->hop == 256) return launch_istft_reg_t<16, 4>(p, d_S, nsrc, nframes, ldf, src_stride, d_out, Lout, out_stride, st);
+  DCS_REQUIRE(false, "istft_reg: unsupported frame size / hop");
+}
+
+}  // namespace dcs

@@ -161,9 +161,9 @@ def relu(x):
 
 
 # ----------------------------------------------------------------------------- networks
-def predict(params, x, arch):
+def predict(params, x, arch, return_pre=False):
     """`lasagne.layers.get_output(build_ca(...), deterministic=True)`: x [B,nch,tc,F] ->
-    rectified concat output [B, nout, tc, F]."""
+    rectified concat output [B, nout, tc, F] (return_pre: the value before the final rectify)."""
     a = ARCHS[arch]
     p = [np.asarray(v, dtype=np.float64) for v in params]
     x = np.asarray(x, dtype=np.float64)
@@ -184,7 +184,18 @@ def predict(params, x, arch):
             g = maxpool_w_inverse(g, h1, a["pool"])                      # InverseLayer(., pool1)
         decs.append(conv2d_inverse(g, W1, x.shape, s1))                  # InverseLayer(., conv1)
     merged = np.concatenate([decs[i] for i in a["dec_of_out"]], axis=1)  # ConcatLayer(axis=1)
-    return relu(merged + p[-1][None, :, None, None])                     # BiasLayer + rectify
+    pre = merged + p[-1][None, :, None, None]                            # BiasLayer
+    return pre if return_pre else relu(pre)                              # + rectify
+
+
+def near_kink(pre, rule, nsrc, tau=2e-8):
+    """Bins where the reference's soft mask is DISCONTINUOUS and the float64 value sits within
+    `tau` of the jump: all rectified outputs vanish on one side ('dsd' rule: masks jump from
+    (1/nsrc, ...) to (1, 0, ...); 'bach10' rule: from 0 to 1).  No finite-precision evaluation
+    can be expected to land on the oracle's side there."""
+    s = np.sort(pre[:, :nsrc], axis=1)
+    top, second = s[:, -1], s[:, -2]
+    return (np.abs(top) < tau) & (second <= tau)
 
 
 def soft_masks(pred, rule, nsrc, rand=None):

@@ -29,7 +29,7 @@ def decode_wav_array(audioObj, family="dsd"):
 
 def separate(audio, params, arch, frameSize=1024, hopSize=512, window=np.hanning,
              scale_factor=0.3, time_context=30, overlap=25, batch_size=32,
-             patcher="standalone", return_spec=False):
+             patcher="standalone", return_spec=False, count_kinks=False):
     """mono float64 audio [L] (or, for arch 'bach10_score', a callable building the 4-channel
     input from the scaled magnitude) -> stems float64 [nsrc, L]."""
     a = nets.ARCHS[arch]
@@ -41,6 +41,13 @@ def separate(audio, params, arch, frameSize=1024, hopSize=512, window=np.hanning
                            overlap=overlap, batch_size=batch_size)
     output = [nets.predict_function2(params, b, arch) for b in batches]
     output = np.array(output)                            # [nb, nsrc, B, 1, tc, F]
+    if count_kinks:
+        nk, left = 0, nchunks
+        for b in batches:
+            pre = nets.predict(params, b, arch, return_pre=True)[:max(0, min(left, batch_size))]
+            nk += int(nets.near_kink(pre, a["mask"], a["nsrc"]).sum())
+            left -= batch_size
+        separate.last_kinks = nk
     if nchunks == 0:
         mm = np.zeros((a["nsrc"], len(ph), mag.shape[-1]))
     else:
