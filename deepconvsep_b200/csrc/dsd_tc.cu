@@ -12,7 +12,7 @@
 //   A = W1t tile [128 bins][K]  (weights; split hi/lo into shared memory ONCE per CTA)
 //   B = G rows   [144][K]       (decoder activations; loaded, split and staged per tile)
 // Persistent CTAs: a CTA owns one 128-bin tile and a contiguous range of 8-frame groups.
-//   warps 0-15 epilogue | warp 16 MMA issue + TMEM alloc | warps 17-20 B producers
+//   warps 0-15 epilogue | warp 16 MMA issue + TMEM alloc | warps 17-24 B producers
 // (16 epilogue warps: a single warp per scheduler runs the dependent mask arithmetic at
 //  IPC ~0.2 -- measured, profiles/r1_notes.md -- so each scheduler gets four.)
 // Double-buffered B stages and TMEM accumulators: the MMAs of group g+1 overlap the epilogue
@@ -32,14 +32,16 @@ constexpr int MT_COLS = MT_FRAMES * MT_SLOTS * 3;  // 144
 constexpr int MT_C1 = 50;
 constexpr int MT_KSTEPS = 7;             // ceil(50 / 8)
 constexpr int MT_EPI_WARPS = 16;          // 4 per TMEM lane quadrant, 2 frames of a group each
-constexpr int MT_THREADS = (MT_EPI_WARPS + 1 + 4) * 32;  // 672
+constexpr int MT_PROD_WARPS = 8;
+constexpr int MT_PROD = MT_PROD_WARPS * 32;             // 256 producer threads
+constexpr int MT_THREADS = (MT_EPI_WARPS + 1 + MT_PROD_WARPS) * 32;  // 800
 constexpr int MT_A_SUB = MT_BINS * ROW_BYTES;      // 16 KB: [128][32] fp32
 constexpr int MT_B_SUB = MT_COLS * ROW_BYTES;      // 18 KB: [144][32] fp32
 constexpr int MT_A_BYTES = 4 * MT_A_SUB;           // hi k0-31, hi k32-63, lo k0-31, lo k32-63
 constexpr int MT_B_STAGE = 4 * MT_B_SUB;           // same four planes
 constexpr int MT_BAR_OFF = MT_A_BYTES + 2 * MT_B_STAGE;
 constexpr int MT_TAB_OFF = MT_BAR_OFF + 128;       // int64 source-row offsets of the 144 B rows
-constexpr int MT_SMEM = MT_TAB_OFF + MT_COLS * 8 + 1024;  // + alignment slack
+constexpr int MT_SMEM = MT_TAB_OFF + 2 * MT_COLS * 8 + 1024;  // two row tables + alignment slack
 constexpr uint32_t MT_TMEM_COLS = 512;
 
 __global__ void __launch_bounds__(MT_THREADS, 1)
@@ -63,7 +65,7 @@ dsd_mask_tc_kernel(const DsdMaskArgs a, int groups_per_cta, int num_groups) {
 
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&full_b[s], 128);
+      mbar_init(&full_b[s], MT_PROD);
       mbar_init(&empty_b[s], 1);
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], MT_EPI_WARPS * 32);
@@ -98,11 +100,14 @@ dsd_mask_tc_kernel(const DsdMaskArgs a, int groups_per_cta, int num_groups) {
 
   if (warp > MT_EPI_WARPS) {
     // ------------------------------------------------------------------ B producers
-    const int pt = tid - (MT_EPI_WARPS + 1) * 32;  // 0..127
-    for (int g = g_begin; g < g_end; ++g) {
-      const int it = g - g_begin, s = it & 1;
-      // source row (float offset into G, -1 = zero row) of each of the 144 B rows of this group
-      for (int rr = pt; rr < MT_COLS; rr += 128) {
+    const int pt = tid - (MT_EPI_WARPS + 1) * 32;  // 0..255
+    // Each group stages 144 rows x 16 chunks of 16 B (13 real, the rest zero) = 9 chunks per
+    // thread: 8 consecutive threads read one row's consecutive chunks (coalesced) and write 8
+    // distinct swizzled slots.  The loads of group g+1 are in flight while group g is split,
+    // stored and consumed; the source-row table is double buffered (one bar.sync per group).
+    constexpr int CPT = MT_COLS * 16 / MT_PROD;  // 9
+    auto build_table = [&](int g, int64_t* tab) {
+      for (int rr = pt; rr < MT_COLS; rr += MT_PROD) {
         const int f = rr / 18, rem = rr - f * 18, j = rem / 3, d = rem - j * 3;
         const int t = g * MT_FRAMES + f;
         int64_t src = -1;
@@ -114,42 +119,47 @@ dsd_mask_tc_kernel(const DsdMaskArgs a, int groups_per_cta, int num_groups) {
           const int k = k_lo + j;
           if (k <= k_hi) src = ((int64_t)(k * 3 + d) * a.tc + (t - k * step)) * a.ldg;
         }
-        row_src[rr] = src;
+        tab[rr] = src;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // producers only
+    };
+    float4 v[CPT];
+    auto issue_loads = [&](const int64_t* tab) {
+#pragma unroll
+      for (int u = 0; u < CPT; ++u) {
+        const int idx = u * MT_PROD + pt;
+        const int rr = idx >> 4, c4 = idx & 15;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c4 < 13) {
+          const int64_t src = tab[rr];
+          if (src >= 0) v[u] = __ldg(reinterpret_cast<const float4*>(a.G + src) + c4);
+        }
+      }
+    };
+    if (g_begin < g_end) {
+      build_table(g_begin, row_src);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      issue_loads(row_src);
+    }
+    for (int g = g_begin; g < g_end; ++g) {
+      const int it = g - g_begin, s = it & 1;
+      if (g + 1 < g_end) build_table(g + 1, row_src + ((it + 1) & 1) * MT_COLS);
       mbar_wait(&empty_b[s], ((it >> 1) & 1) ^ 1);
       uint8_t* st = sB + s * MT_B_STAGE;
-      // 144 rows x 16 chunks of 16 B (13 real, the rest zero): 8 consecutive threads read one
-      // row's consecutive chunks (coalesced), and write 8 distinct swizzled slots of that row.
-      constexpr int TOTAL = MT_COLS * 16;           // 2304 = 18 * 128
-#pragma unroll 1
-      for (int base = 0; base < TOTAL; base += 128 * 6) {
-        float4 v[6];
 #pragma unroll
-        for (int u = 0; u < 6; ++u) {
-          const int idx = base + u * 128 + pt;      // < TOTAL always (18 = 3 * 6 passes)
-          const int rr = idx >> 4, c4 = idx & 15;
-          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (c4 < 13) {
-            const int64_t src = row_src[rr];
-            if (src >= 0) v[u] = __ldg(reinterpret_cast<const float4*>(a.G + src) + c4);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 6; ++u) {
-          const int idx = base + u * 128 + pt;
-          const int rr = idx >> 4, c4 = idx & 15;
-          if (c4 == 12) { v[u].z = 0.f; v[u].w = 0.f; }  // columns 50, 51 of the padded G row
-          float4 hi, lo;
-          split4(v[u], hi, lo);
-          const uint32_t off = (c4 >> 3) * MT_B_SUB + tile_off(rr, c4 & 7);
-          *reinterpret_cast<float4*>(st + off) = hi;
-          *reinterpret_cast<float4*>(st + 2 * MT_B_SUB + off) = lo;
-        }
+      for (int u = 0; u < CPT; ++u) {
+        const int idx = u * MT_PROD + pt;
+        const int rr = idx >> 4, c4 = idx & 15;
+        if (c4 == 12) { v[u].z = 0.f; v[u].w = 0.f; }  // columns 50, 51 of the padded G row
+        float4 hi, lo;
+        split4(v[u], hi, lo);
+        const uint32_t off = (c4 >> 3) * MT_B_SUB + tile_off(rr, c4 & 7);
+        *reinterpret_cast<float4*>(st + off) = hi;
+        *reinterpret_cast<float4*>(st + 2 * MT_B_SUB + off) = lo;
       }
       fence_proxy_async();
       mbar_arrive(&full_b[s]);
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // row_src is rewritten next iteration
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // next table complete, this one no longer read
+      if (g + 1 < g_end) issue_loads(row_src + ((it + 1) & 1) * MT_COLS);
     }
   } else if (warp == MT_EPI_WARPS) {
     // ------------------------------------------------------------------ MMA issuer
@@ -233,7 +243,7 @@ dsd_mask_tc_kernel(const DsdMaskArgs a, int groups_per_cta, int num_groups) {
             const float p2 = fmaxf(y[ff][3 * j + 2] + bo2, 0.f), p3 = fmaxf(y[ff][3 * j + 1] + bo3, 0.f);
             const float tot = (p0 + p1) + (p2 + p3);
             const bool pos = tot > 0.f;
-            const float r = pos ? up / tot : 0.f;        // up * mask = p * (up / tot)
+            const float r = pos ? __fdividef(up, tot) : 0.f;  // up * mask = p * (up / tot); MUFU.RCP, 2 ulp
             const float q = pos ? 0.f : 0.25f * up;      // all-zero bin: 1/4 each
             acc[ff][0] = fmaf(down, acc[ff][0], fmaf(p0, r, q));
             acc[ff][1] = fmaf(down, acc[ff][1], fmaf(p1, r, q));

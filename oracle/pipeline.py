@@ -41,17 +41,26 @@ def separate(audio, params, arch, frameSize=1024, hopSize=512, window=np.hanning
                            overlap=overlap, batch_size=batch_size)
     output = [nets.predict_function2(params, b, arch) for b in batches]
     output = np.array(output)                            # [nb, nsrc, B, 1, tc, F]
+    kink_energy = 0.0
     if count_kinks:
         nk, left = 0, nchunks
         for b in batches:
-            pre = nets.predict(params, b, arch, return_pre=True)[:max(0, min(left, batch_size))]
-            nk += int(nets.near_kink(pre, a["mask"], a["nsrc"]).sum())
+            nb = max(0, min(left, batch_size))
+            pre = nets.predict(params, b, arch, return_pre=True)[:nb]
+            flag = nets.near_kink(pre, a["mask"], a["nsrc"])           # [nb, tc, F]
+            nk += int(flag.sum())
+            kink_energy += float((flag * b[:nb].sum(axis=1) ** 2).sum())
             left -= batch_size
         separate.last_kinks = nk
     if nchunks == 0:
         mm = np.zeros((a["nsrc"], len(ph), mag.shape[-1]))
     else:
         mm = patch.overlapadd_multi(output, batches, nchunks, overlap=overlap)
+    if count_kinks:
+        # worst-case relative error a flip of every flagged bin can cause, per stem: the mask of a
+        # flagged bin moves by at most 1, so the blended magnitude moves by at most the mixture's
+        separate.last_kink_bound = [float(np.sqrt(kink_energy / max(float((mm[i] ** 2).sum()), 1e-300)))
+                                    for i in range(a["nsrc"])]
     stems = []
     for i in range(a["nsrc"]):
         m = mm[i, :len(ph)]

@@ -1,0 +1,91 @@
+"""GPU: the reference-named Python entry points (transform.transformFFT, stft_norm/istft_norm,
+separate_dsd.train_auto/main) against the oracle.  fp32 device arithmetic vs float64 reference:
+2e-6 relative L2 on spectra / magnitudes, 5e-6 on reconstructed audio."""
+import os
+import numpy as np
+import pytest
+import scipy.io.wavfile
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import dsp, nets, pipeline  # noqa: E402
+
+
+def rel(a, b):
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def test_transformFFT_compute_file_inverse_and_module_functions():
+    from deepconvsep_b200 import transform
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(20000) * 0.1
+    for N, H, win in [(2048, 512, np.hanning), (1024, 256, np.hanning), (4096, 512, dsp.blackmanharris)]:
+        tt = transform.transformFFT(frameSize=N, hopSize=H, sampleRate=44100, window=win)
+        mag, ph = tt.compute_file(x, phase=True)
+        mag_r, ph_r = dsp.compute_file(x, phase=True, frameSize=N, hopSize=H, window=win)
+        assert mag.dtype == np.float64 and mag.shape == mag_r.shape == ph.shape
+        assert rel(mag, mag_r) < 2e-6
+        assert rel(mag * np.exp(1j * ph), mag_r * np.exp(1j * ph_r)) < 3e-6
+        assert rel(tt.compute_file(x), mag_r) < 2e-6
+        y = tt.compute_inverse(mag_r, ph_r)
+        y_r = dsp.compute_inverse(mag_r, ph_r, frameSize=N, hopSize=H, window=win)
+        assert y.shape == y_r.shape and rel(y[:x.size], y_r[:x.size]) < 5e-6
+        w = win(N)
+        X = transform.stft_norm(x, window=w, hopsize=float(H), nfft=float(N))
+        X_r = dsp.stft_norm(x, window=w, hopsize=float(H), nfft=float(N))
+        assert X.dtype == np.complex128 and rel(X, X_r) < 2e-6
+        y2 = transform.istft_norm(X_r, window=w, analysisWindow=w, hopsize=float(H), nfft=float(N))
+        assert rel(y2[:x.size], x) < 5e-6
+        # distinct synthesis / analysis windows (istft_norm's general signature)
+        ws = transform.sinebell(N)
+        y3 = transform.istft_norm(X_r, window=ws, analysisWindow=w, hopsize=float(H), nfft=float(N))
+        y3_r = dsp.istft_norm(X_r, window=ws, analysisWindow=w, hopsize=float(H), nfft=float(N))
+        assert rel(y3[:x.size], y3_r[:x.size]) < 5e-6
+
+
+def test_compute_transform_dump(tmp_path):
+    from deepconvsep_b200 import transform
+    rng = np.random.default_rng(2)
+    audio = rng.standard_normal((6000, 3)) * 0.1
+    tt = transform.transformFFT(frameSize=1024, hopSize=512, suffix="f")
+    mags = tt.compute_transform(audio, phase=False, save=False)
+    assert mags.shape == (3, dsp.num_frames(6000, 512), 513)
+    out = str(tmp_path / "song.data")
+    assert tt.compute_transform(audio, out_path=out, phase=True, save=True) is None
+    m = np.fromfile(str(tmp_path / "song_f_m_.data")).reshape(tt.get_shape(str(tmp_path / "song_f_m_.shape")))
+    np.testing.assert_array_equal(m, mags)
+    for i in range(3):
+        assert rel(m[i], dsp.compute_file(audio[:, i], frameSize=1024, hopSize=512)) < 2e-6
+    assert os.path.exists(str(tmp_path / "song_f_p_.data"))
+
+
+def test_separate_dsd_cli_end_to_end(tmp_path):
+    """python separate_dsd.py -i mix.wav -o out -m model.pkl  ==  oracle train_auto, to 1 LSB."""
+    from deepconvsep_b200 import save_model
+    from deepconvsep_b200.examples.dsd100 import separate_dsd
+    params = nets.make_synthetic_params("dsd", 513, seed=21)
+    pkl = str(tmp_path / "model.pkl")
+    save_model(pkl, params)
+    mix, _ = pipeline.synth_mixture(2.5, 33)
+    rng = np.random.default_rng(3)
+    pcm = np.stack([np.round(mix * 30000).astype(np.int16),
+                    np.round((0.8 * mix + 0.01 * rng.standard_normal(mix.size)) * 30000).astype(np.int16)], axis=1)
+    wav = str(tmp_path / "mix.wav")
+    scipy.io.wavfile.write(wav, 44100, pcm)
+    outdir = str(tmp_path / "out")
+    os.makedirs(outdir)
+    separate_dsd.main(["-i", wav, "-o", outdir, "-m", pkl])
+    mono = pipeline.decode_wav_array(pcm, "dsd")
+    want = pipeline.separate(mono, params, "dsd", frameSize=1024, overlap=25, count_kinks=True)
+    want16 = (want * 32767).astype("int16")
+    for i, name in enumerate(["vocals", "bass", "drums", "other"]):
+        sr, got = scipy.io.wavfile.read(os.path.join(outdir, name + ".wav"))
+        assert sr == 44100 and got.dtype == np.int16 and got.shape == want16[i].shape
+        d = np.abs(got.astype(np.int32) - want16[i].astype(np.int32))
+        if pipeline.separate.last_kinks == 0:
+            assert d.max() <= 1
+        assert np.mean(d > 1) < 1e-3
+    # wrong sample rate: prints and writes nothing (separate_dsd.py:313)
+    scipy.io.wavfile.write(wav, 22050, pcm)
+    assert separate_dsd.train_auto(wav, outdir, pkl, 0.3, 30, 25, 32, 513) is None

@@ -15,15 +15,18 @@ TOL = 1e-4
 # (oracle.nets.near_kink).  A (patch, frame, bin) whose float64 pre-activation is within 2e-8 of
 # that jump flips in ANY fp32 evaluation and moves one time-frequency bin by up to 75 % of the
 # mixture; on a few-second clip a single flip is ~5e-4 relative L2, on a 20 s clip it is below
-# the 1e-4 budget again (test_medium_clip_parity).  Short-clip cases therefore accept
-# TOL_KINK when -- and only when -- the oracle itself reports such bins.
-TOL_KINK = 2e-3
+# the 1e-4 budget again (test_medium_clip_parity).  Short-clip cases therefore add, per stem,
+# the worst-case error of the bins the ORACLE flags (each flagged bin's mask may move by <= 1):
+# sqrt(sum_flagged |mix|^2 / sum |stem|^2), computed by oracle.pipeline -- zero when nothing is
+# flagged, so the strict bar applies whenever the oracle is well conditioned.
 
 
-def check_stems(got, want, kinks):
-    worst = max(rel(got[s].astype(np.float64), want[s]) for s in range(want.shape[0]))
-    assert worst <= (TOL if kinks == 0 else TOL_KINK), (worst, kinks)
-    return worst
+def check_stems(got, want, kinks, bound=None):
+    errs = [rel(got[s].astype(np.float64), want[s]) for s in range(want.shape[0])]
+    for s, e in enumerate(errs):
+        allow = TOL if not kinks else TOL + 1.5 * bound[s]
+        assert e <= allow, (s, e, allow, kinks)
+    return max(errs)
 
 
 def rel(a, b):
@@ -50,12 +53,12 @@ def test_separate_matches_oracle(N, seconds, overlap, patcher):
     mix, stems = pipeline.synth_mixture(seconds, 1000 + N)
     want = pipeline.separate(mix, params, "dsd", frameSize=N, hopSize=hop, window=np.hanning, overlap=overlap,
                              patcher=patcher, count_kinks=True)
-    kinks = pipeline.separate.last_kinks
+    kinks, bound = pipeline.separate.last_kinks, pipeline.separate.last_kink_bound
     got = sep.separate(mix)
     assert got.shape == want.shape and got.dtype == np.float32
     # the synthetic weights must exercise every source (no constant masks)
     assert min(np.linalg.norm(want[s]) for s in range(4)) > 0.02 * np.linalg.norm(mix)
-    check_stems(got, want, kinks)
+    check_stems(got, want, kinks, bound)
     for s in range(4):
         assert abs(sdr(stems[s], got[s]) - sdr(stems[s], want[s])) <= 0.01
     # the device-buffer entry point gives the same bits as the host-buffer one
