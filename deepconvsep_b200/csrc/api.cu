@@ -364,8 +364,12 @@ static int dsd_forward(dcs_ctx* ctx, dcs_model* m, const float* d_mag, const flo
   g4.n_seg = h2 * C2; g4.n_ss = (int64_t)HP * C2; g4.c_col0 = (int64_t)(kh2 - 1) * C2;
   { ProfScope ps(ctx, "dec_dense_gemm", st); DCS_TRY(run_gemm(ctx, g4, m->tWdec, st)); }
   // InverseLayer(conv2): full correlation on the padded activations, rows (k, d, u)
+  // Rows are ordered (u, k, d) -- u-major -- so that a 128-row tile holds one or two output positions
+  // u and can skip the taps that only see the zero padding (on average 8 of the 15).
   GemmDesc g5 = gemm_plain(ap, 0, m->Wt2, C1, nullptr, G, ldg, (int)(P * 3 * tc), C1, kh2 * C2, 0);
-  g5.m_inner = tc; g5.a_so = (int64_t)HP * C2; g5.a_si = C2;
+  g5.m_inner = (int)(P * 3); g5.a_so = C2; g5.a_si = (int64_t)HP * C2;
+  g5.cm_inner = (int)(P * 3); g5.c_so = ldg; g5.c_si = (int64_t)tc * ldg;
+  g5.kc_rows = (int)(P * 3); g5.kc_unit = C2; g5.kc_pad = kh2 - 1; g5.kc_n = h2; g5.kc_taps = kh2;
   { ProfScope ps(ctx, "dec_convT2_gemm", st); DCS_TRY(run_gemm(ctx, g5, m->tWt2, st)); }
   // InverseLayer(conv1) + bias + ReLU + mask + cross-fade + phase
   DsdMaskArgs a;

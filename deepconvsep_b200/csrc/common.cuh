@@ -122,6 +122,11 @@ struct GemmDesc {
   int cm_inner; int64_t c_so, c_si;  // C row offset
   int n_seg; int64_t n_ss, c_col0;   // C col offset  = c_col0 + (n / n_seg) * n_ss + (n % n_seg)
   int relu;
+  // optional K clipping for transposed convolutions on a zero-padded operand: rows are grouped by
+  // output position u = m / kc_rows; only taps q with kc_pad <= u + q < kc_pad + kc_n touch
+  // non-zero input, so a tile skips the k-blocks outside [kc_unit*q_lo, kc_unit*(q_hi+1)).
+  // kc_rows = 0 disables it.  (Pure optimisation: the skipped products are exact zeros.)
+  int kc_rows, kc_unit, kc_pad, kc_n, kc_taps;
 };
 GemmDesc gemm_plain(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C,
                     int64_t ldc, int M, int N, int K, int relu);

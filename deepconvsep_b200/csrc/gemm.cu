@@ -109,6 +109,7 @@ GemmDesc gemm_plain(const float* A, int64_t lda, const float* B, int64_t ldb, co
   d.cm_inner = 1; d.c_so = ldc; d.c_si = 0;
   d.n_seg = N > 0 ? N : 1; d.n_ss = 0; d.c_col0 = 0;
   d.relu = relu;
+  d.kc_rows = 0; d.kc_unit = d.kc_pad = d.kc_n = d.kc_taps = 0;
   return d;
 }
 

@@ -20,7 +20,9 @@ namespace dcs {
 using namespace tc;
 
 constexpr int TC_BM = 128;
-constexpr int TC_THREADS = 160;
+constexpr int TC_PGROUPS = 2;                 // producer groups of 4 warps, alternating stages
+constexpr int TC_MMA_WARP = 4 * TC_PGROUPS;
+constexpr int TC_THREADS = (TC_MMA_WARP + 1) * 32;  // 288
 
 template <int BN, int STAGES>
 struct TcSmem {
@@ -50,7 +52,15 @@ gemm_tc_kernel(const GemmDesc d, const float* __restrict__ Bhi, const float* __r
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
-  const int num_kb = (d.K + KSTAGE - 1) / KSTAGE;
+  int kb_lo = 0, kb_hi = (d.K + KSTAGE - 1) / KSTAGE;
+  if (d.kc_rows > 0) {
+    const int u_min = m0 / d.kc_rows, u_max = min(d.M - 1, m0 + TC_BM - 1) / d.kc_rows;
+    const int q_lo = max(0, d.kc_pad - u_max), q_hi = min(d.kc_taps - 1, d.kc_pad + d.kc_n - 1 - u_min);
+    kb_lo = (d.kc_unit * q_lo) / KSTAGE;
+    kb_hi = min(kb_hi, (d.kc_unit * (q_hi + 1) + KSTAGE - 1) / KSTAGE);
+    if (kb_hi <= kb_lo) kb_hi = kb_lo + 1;   // keep one (all-zero) block so the accumulators are defined
+  }
+  const int num_kb = kb_hi - kb_lo;   // k-block i of this tile is global block kb_lo + i
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -64,14 +74,17 @@ gemm_tc_kernel(const GemmDesc d, const float* __restrict__ Bhi, const float* __r
   const int n_main = acc_mode == 2 ? 3 : 1;
   const int corr_acc = acc_mode == 0 ? 0 : n_main;       // accumulator index of the corrections
   const int n_main_used = min(n_main, num_kb * (KSTAGE / 8));
-  if (warp == 4) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == TC_MMA_WARP) tmem_alloc(tmem_slot, TMEM_COLS);
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
+  if (warp < TC_MMA_WARP) {
     // ------------------------------------------------------------------ producers
+    // group pg stages k-blocks pg, pg+2, ...: two stage loads are in flight per CTA
+    const int pg = warp >> 2;
+    const int tid = threadIdx.x & 127, warp = tid >> 5;   // index inside the producer group
     // Each warp-wide load covers whole 128-byte rows (AVEC=4: 4 rows x 8 chunks of 16 B per
     // instruction, AVEC=2: 2 rows x 16 pieces of 8 B, AVEC=1: 1 row x 32 floats) so global reads
     // are coalesced, and the swizzled shared stores of one row hit 8 distinct 16-byte slots.
@@ -95,7 +108,7 @@ gemm_tc_kernel(const GemmDesc d, const float* __restrict__ Bhi, const float* __r
     auto gload = [&](int kb) {
 #pragma unroll
       for (int i = 0; i < NI; ++i) {
-        const int k = kb * KSTAGE + piece * AVEC;
+        const int k = (kb_lo + kb) * KSTAGE + piece * AVEC;
 #pragma unroll
         for (int e = 0; e < AVEC; ++e) ra[i][e] = 0.f;
         if (row_ok[i] && k < d.K) {
@@ -118,12 +131,12 @@ gemm_tc_kernel(const GemmDesc d, const float* __restrict__ Bhi, const float* __r
       for (int i = 0; i < NBI; ++i) {
         const int rr = i * 16 + (tid >> 3);          // row in the stacked (hi, lo) B planes
         const int which = rr / BN, rn = rr - which * BN;
-        const float* src = (which ? Blo : Bhi) + (int64_t)(n0 + rn) * Kp + kb * KSTAGE + 4 * (tid & 7);
-        rb[i] = __ldg(reinterpret_cast<const float4*>(src));
+        const float* src = (which ? Blo : Bhi) + (int64_t)(n0 + rn) * Kp + (kb_lo + kb) * KSTAGE + 4 * (tid & 7);
+        rb[i] = ld_stream(reinterpret_cast<const float4*>(src));
       }
     };
-    gload(0);
-    for (int kb = 0; kb < num_kb; ++kb) {
+    if (pg < num_kb) gload(pg);
+    for (int kb = pg; kb < num_kb; kb += TC_PGROUPS) {
       const int s = kb % STAGES;
       const uint32_t par = (kb / STAGES) & 1;
       mbar_wait(&empty[s], par ^ 1);
@@ -155,9 +168,10 @@ gemm_tc_kernel(const GemmDesc d, const float* __restrict__ Bhi, const float* __r
       }
       fence_proxy_async();
       mbar_arrive(&full[s]);
-      if (kb + 1 < num_kb) gload(kb + 1);
+      if (kb + TC_PGROUPS < num_kb) gload(kb + TC_PGROUPS);
     }
-    const int r = tid;           // epilogue: thread = output row = TMEM lane
+    if (pg == 0) {               // epilogue: warps 0-3, thread = output row = TMEM lane
+    const int r = tid;
     const int m = m0 + r;
     const int mc = m < d.M ? m : 0;
     // ------------------------------------------------------------------ epilogue
@@ -196,6 +210,7 @@ gemm_tc_kernel(const GemmDesc d, const float* __restrict__ Bhi, const float* __r
         }
       }
     }
+    }
     fence_before_sync();
   } else if (lane == 0) {
     // ------------------------------------------------------------------ MMA issuer
@@ -224,7 +239,7 @@ gemm_tc_kernel(const GemmDesc d, const float* __restrict__ Bhi, const float* __r
     umma_commit(tmem_full);
   }
   __syncthreads();
-  if (warp == 4) {
+  if (warp == TC_MMA_WARP) {
     fence_after_sync();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
@@ -288,13 +303,13 @@ int launch_gemm_tc(dcs_ctx* ctx, const GemmDesc& d, const TcWeight& w, cudaStrea
   };
   if (aligned(4)) avec = 4; else if (aligned(2)) avec = 2;
   if (d.N > 64) {
-    if (avec == 4) return launch_tc<128, 2, 4>(ctx, d, w, st);
-    if (avec == 2) return launch_tc<128, 2, 2>(ctx, d, w, st);
-    return launch_tc<128, 2, 1>(ctx, d, w, st);
+    if (avec == 4) return launch_tc<128, 3, 4>(ctx, d, w, st);
+    if (avec == 2) return launch_tc<128, 3, 2>(ctx, d, w, st);
+    return launch_tc<128, 3, 1>(ctx, d, w, st);
   }
-  if (avec == 4) return launch_tc<64, 2, 4>(ctx, d, w, st);
-  if (avec == 2) return launch_tc<64, 2, 2>(ctx, d, w, st);
-  return launch_tc<64, 2, 1>(ctx, d, w, st);
+  if (avec == 4) return launch_tc<64, 4, 4>(ctx, d, w, st);
+  if (avec == 2) return launch_tc<64, 4, 2>(ctx, d, w, st);
+  return launch_tc<64, 4, 1>(ctx, d, w, st);
 }
 
 }  // namespace dcs

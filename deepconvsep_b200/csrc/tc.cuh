@@ -132,6 +132,14 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// streaming 16-byte load: read-only path, no L1 allocation (weights pass through once per CTA and
+// must not evict the activation rows that overlapping convolution views re-read)
+__device__ __forceinline__ float4 ld_stream(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
 // ---- 3xTF32 operand split ---------------------------------------------------------------------
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
