@@ -46,7 +46,7 @@ void DevBuf::release() {
   cap = 0;
 }
 
-static int upload(const std::vector<float>& h, float** d) {
+int upload(const std::vector<float>& h, float** d) {
   DCS_CUDA(cudaMalloc((void**)d, h.size() * sizeof(float)));
   DCS_CUDA(cudaMemcpy(*d, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
   return DCS_OK;
@@ -61,19 +61,6 @@ int64_t dcs_ctx::workspace_bytes() const {
   for (const auto& b : net) s += b.cap;
   return (int64_t)s;
 }
-
-// ------------------------------------------------------------------------------------ model
-struct dcs_model {
-  dcs_ctx* ctx;
-  int arch, F, tc, nsrc;
-  // DSD dims
-  int C1, C2, kh2, h2, nfc, ndec;
-  int64_t ldw;
-  std::vector<float*> dev;  // owned device arrays
-  float *W1f, *b1, *W2c, *b2, *Wfc, *bfc, *Wdec, *bdec, *Wt2, *W1t, *bout;
-  // tensor-core copies of the GEMM weights (K-major, 3xTF32 split)
-  dcs::TcWeight tW1f, tW2c, tWfc, tWdec, tWt2;
-};
 
 extern "C" {
 
@@ -230,6 +217,7 @@ int dcs_model_nsources(const dcs_model* m) { return m ? m->nsrc : 0; }
 int dcs_model_destroy(dcs_model* m) {
   if (!m) return DCS_OK;
   for (float* d : m->dev) cudaFree(d);
+  for (auto& w : m->sc.tW) tc_weight_destroy(&w);
   tc_weight_destroy(&m->tW1f); tc_weight_destroy(&m->tW2c); tc_weight_destroy(&m->tWfc);
   tc_weight_destroy(&m->tWdec); tc_weight_destroy(&m->tWt2);
   delete m;
@@ -314,6 +302,9 @@ int dcs_model_create(dcs_ctx* ctx, int arch, int feat_size, int time_context, in
   int r;
   switch (arch) {
     case DCS_ARCH_DSD: r = model_create_dsd(m, nparams, h_params, shapes, ndims); break;
+    case DCS_ARCH_IKALA:
+    case DCS_ARCH_IKALA_NOPOOL:
+    case DCS_ARCH_BACH10: r = model_create_sconv(m, nparams, h_params, shapes, ndims); break;
     default:
       set_error("dcs_model_create: architecture %d has no CUDA path yet", arch);
       r = DCS_EINVAL;
@@ -342,11 +333,13 @@ static int dsd_forward(dcs_ctx* ctx, dcs_model* m, const float* d_mag, const flo
   const int64_t Tp = std::max<int64_t>(T, (P - 1) * step + tc);
   const int HP = h2 + 2 * (kh2 - 1), ldg = (C1 + 3) / 4 * 4;
   DevBuf &bH1 = ctx->net[0], &bH2 = ctx->net[1], &bz = ctx->net[2], &bap = ctx->net[3], &bG = ctx->net[4];
-  DCS_TRY(bH1.ensure((size_t)Tp * C1 * 4, st));
-  DCS_TRY(bH2.ensure((size_t)(Tp - kh2 + 1) * C2 * 4, st));
-  DCS_TRY(bz.ensure((size_t)P * nfc * 4, st));
-  DCS_TRY(bap.ensure((size_t)P * 3 * HP * C2 * 4, st));  // zero on (re)allocation; only the interior is ever written
-  DCS_TRY(bG.ensure((size_t)P * 3 * tc * ldg * 4, st));
+  const uint64_t sig = ((uint64_t)(DCS_ARCH_DSD + 1) << 48) ^ ((uint64_t)m->F << 24) ^ (uint64_t)(tc * 64);
+  DCS_TRY(ensure_layout(ctx, 0, (size_t)Tp * C1 * 4, sig, st));
+  DCS_TRY(ensure_layout(ctx, 1, (size_t)(Tp - kh2 + 1) * C2 * 4, sig, st));
+  DCS_TRY(ensure_layout(ctx, 2, (size_t)P * nfc * 4, sig, st));
+  // zero on (re)allocation or layout change; afterwards only the interior rows are ever written
+  DCS_TRY(ensure_layout(ctx, 3, (size_t)P * 3 * HP * C2 * 4, sig, st));
+  DCS_TRY(ensure_layout(ctx, 4, (size_t)P * 3 * tc * ldg * 4, sig, st));
   float *H1 = bH1.as<float>(), *H2 = bH2.as<float>(), *z = bz.as<float>(), *ap = bap.as<float>(), *G = bG.as<float>();
 
   // conv1 + both biases, once per frame (kernel height 1): H1[Tp][C1] = mag[T][F] * W1f
@@ -392,6 +385,11 @@ int dcs_separate_spec(dcs_ctx* ctx, dcs_model* m, const float* d_mag, const dcs_
     case DCS_ARCH_DSD:
       return dsd_forward(ctx, m, d_mag, (const float2*)d_X, T, ldf, overlap, patcher, (float2*)d_S, src_stride,
                          (cudaStream_t)stream);
+    case DCS_ARCH_IKALA:
+    case DCS_ARCH_IKALA_NOPOOL:
+    case DCS_ARCH_BACH10:
+      return sconv_forward(ctx, m, d_mag, (const float2*)d_X, T, ldf, overlap, patcher, (float2*)d_S, src_stride,
+                           (cudaStream_t)stream);
   }
   DCS_REQUIRE(false, "architecture %d has no CUDA path yet", m->arch);
 }

@@ -67,6 +67,7 @@ struct dcs_ctx {
   // workspace of one in-flight pipeline
   dcs::DevBuf audio, X, mag, S, stems, pcm_in, pcm_out;
   dcs::DevBuf net[12];
+  uint64_t net_sig[12] = {0};   // layout signature of what each net[] buffer currently holds
   int64_t workspace_bytes() const;
 };
 
@@ -95,6 +96,42 @@ struct ProfScope {
 };
 }  // namespace dcs
 
+namespace dcs {
+// weight matrix prepared for the tensor-core path: K-major, zero padded, split for 3xTF32
+struct TcWeight {
+  float* hi = nullptr;
+  float* lo = nullptr;
+  int K = 0, N = 0, Kp = 0, Np = 0;
+};
+}  // namespace dcs
+
+// ---- model (device-resident network)
+struct dcs_sconv {   // strided-conv1 families: iKala (pool / no pool), Bach10
+  int nch, sw1, J, pool, WP, kh2, kw2, h2, w2, HP, WPP, ndec, nfc, rule;
+  dcs::TcWeight tW[8];                 // 0 conv1, 1 conv2, 2 fc, 3 convT2, 4.. decoder dense layers
+  float *b1, *b2, *bfc, *bdec[4], *bout, *Wsc;
+};
+struct dcs_model {
+  dcs_ctx* ctx;
+  int arch, F, tc, nsrc;
+  // DSD dims
+  int C1, C2, kh2, h2, nfc, ndec;
+  int64_t ldw;
+  std::vector<float*> dev;  // owned device arrays
+  float *W1f, *b1, *W2c, *b2, *Wfc, *bfc, *Wdec, *bdec, *Wt2, *W1t, *bout;
+  // tensor-core copies of the GEMM weights (K-major, 3xTF32 split)
+  dcs::TcWeight tW1f, tW2c, tWfc, tWdec, tWt2;
+  dcs_sconv sc;
+};
+namespace dcs {
+int upload(const std::vector<float>& h, float** d);
+int model_create_sconv(dcs_model* m, int nparams, const float* const* hp, const int64_t* shp, const int* nd);
+int sconv_forward(dcs_ctx* ctx, dcs_model* m, const float* d_mag, const float2* d_X, int64_t T, int64_t ldf,
+                  int overlap, int patcher, float2* d_S, int64_t src_stride, cudaStream_t st);
+// (re)zero a workspace buffer whenever what it holds changes layout: zero padding is relied upon
+int ensure_layout(dcs_ctx* ctx, int idx, size_t bytes, uint64_t sig, cudaStream_t st);
+}  // namespace dcs
+
 // ---- kernel launchers (each returns a DCS_* code) ---------------------------------------------
 namespace dcs {
 
@@ -116,10 +153,13 @@ struct GemmDesc {
   const float* A; const float* B; const float* bias; float* C;
   int M, N, K;
   int a_valid_rows;          // rows >= a_valid_rows of A read as zeros
-  int m_inner; int64_t a_so, a_si;   // A row offset  = (m / m_inner) * a_so + (m % m_inner) * a_si
+  // A row offset = (m / m_inner) * a_so + ((m % m_inner) / m_inner2) * a_si + (m % m_inner2) * a_s2
+  int m_inner; int64_t a_so, a_si;
+  int m_inner2; int64_t a_s2;
   int k_seg; int64_t k_ss;           // A col offset  = (k / k_seg) * k_ss + (k % k_seg)
   int64_t ldb;                       // B[k][n] at B + k*ldb + n
-  int cm_inner; int64_t c_so, c_si;  // C row offset
+  int cm_inner; int64_t c_so, c_si;  // C row offset (same three-level form)
+  int cm_inner2; int64_t c_s2;
   int n_seg; int64_t n_ss, c_col0;   // C col offset  = c_col0 + (n / n_seg) * n_ss + (n % n_seg)
   int relu;
   // optional K clipping for transposed convolutions on a zero-padded operand: rows are grouped by
@@ -132,12 +172,6 @@ GemmDesc gemm_plain(const float* A, int64_t lda, const float* B, int64_t ldb, co
                     int64_t ldc, int M, int N, int K, int relu);
 int launch_gemm(dcs_ctx* ctx, const GemmDesc& d, cudaStream_t st);
 
-// weight matrix prepared for the tensor-core path: K-major, zero padded, split for 3xTF32
-struct TcWeight {
-  float* hi = nullptr;
-  float* lo = nullptr;
-  int K = 0, N = 0, Kp = 0, Np = 0;
-};
 int tc_weight_create(const float* B_rowmajor, int64_t ldb, int K, int N, TcWeight* out);
 void tc_weight_destroy(TcWeight* w);
 int launch_gemm_tc(dcs_ctx* ctx, const GemmDesc& d, const TcWeight& w, cudaStream_t st);
@@ -155,6 +189,20 @@ struct DsdMaskArgs {
   int only_nyquist;    // FFMA kernel: compute bin F-1 only (the tensor-core kernel did the rest)
 };
 int launch_dsd_mask(dcs_ctx* ctx, const DsdMaskArgs& a, cudaStream_t st);
+// strided-conv1 families (iKala / Bach10): K3s arguments
+struct SconvMaskArgs {
+  int arch;
+  const float* G;       // [P*ndec][tc][WP or J][32] decoder activations after the transposed conv2
+  const uint8_t* tie;   // [T'][WP][32] max-pool tie bits of the forward pass (pooled nets only)
+  const float* W;       // float4 [ND][32]: W[dd][f][r] = conv1.W[f][0][0][KW-1-r-STRIDE*dd]
+  const float* bout;    // [nsrc]
+  const float2* X;      // [T][ldf]
+  float2* S;            // [nsrc][T][ldf]
+  int64_t ldf, src_stride;
+  int T, P, tc, overlap, F, J, WP;
+};
+int launch_pool4(dcs_ctx* ctx, const float* H1, float* Hp, uint8_t* tie, int64_t rows, int J, int WP, cudaStream_t st);
+int launch_sconv_mask(dcs_ctx* ctx, const SconvMaskArgs& a, cudaStream_t st);
 bool dsd_mask_tc_supported(const DsdMaskArgs& a);
 int launch_dsd_mask_tc(dcs_ctx* ctx, const DsdMaskArgs& a, cudaStream_t st);
 

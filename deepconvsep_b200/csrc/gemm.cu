@@ -32,7 +32,7 @@ gemm_f32_kernel(const GemmDesc d) {
     const int m = m0 + tid / BK + 16 * r;
     a_row_ok[r] = (m < d.M) && (m < d.a_valid_rows);
     const int mc = m < d.M ? m : 0;
-    a_row_off[r] = (int64_t)(mc / d.m_inner) * d.a_so + (int64_t)(mc % d.m_inner) * d.a_si;
+    a_row_off[r] = (int64_t)(mc / d.m_inner) * d.a_so + (int64_t)((mc % d.m_inner) / d.m_inner2) * d.a_si + (int64_t)(mc % d.m_inner2) * d.a_s2;
   }
   // B loads: column (tid % 64), rows (tid / 64) + 4 r
   const int bn = n0 + tid % BN;
@@ -84,7 +84,7 @@ gemm_f32_kernel(const GemmDesc d) {
   for (int i = 0; i < TM; ++i) {
     const int m = m0 + ty * TM + i;
     if (m >= d.M) continue;
-    const int64_t roff = (int64_t)(m / d.cm_inner) * d.c_so + (int64_t)(m % d.cm_inner) * d.c_si;
+    const int64_t roff = (int64_t)(m / d.cm_inner) * d.c_so + (int64_t)((m % d.cm_inner) / d.cm_inner2) * d.c_si + (int64_t)(m % d.cm_inner2) * d.c_s2;
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
       const int n = n0 + tx * TN + j;
@@ -103,10 +103,10 @@ GemmDesc gemm_plain(const float* A, int64_t lda, const float* B, int64_t ldb, co
   d.A = A; d.B = B; d.bias = bias; d.C = C;
   d.M = M; d.N = N; d.K = K;
   d.a_valid_rows = M;
-  d.m_inner = 1; d.a_so = lda; d.a_si = 0;
+  d.m_inner = 1; d.a_so = lda; d.a_si = 0; d.m_inner2 = 1; d.a_s2 = 0;
   d.k_seg = K > 0 ? K : 1; d.k_ss = 0;
   d.ldb = ldb;
-  d.cm_inner = 1; d.c_so = ldc; d.c_si = 0;
+  d.cm_inner = 1; d.c_so = ldc; d.c_si = 0; d.cm_inner2 = 1; d.c_s2 = 0;
   d.n_seg = N > 0 ? N : 1; d.n_ss = 0; d.c_col0 = 0;
   d.relu = relu;
   d.kc_rows = 0; d.kc_unit = d.kc_pad = d.kc_n = d.kc_taps = 0;
@@ -115,14 +115,14 @@ GemmDesc gemm_plain(const float* A, int64_t lda, const float* B, int64_t ldb, co
 
 int launch_gemm(dcs_ctx* ctx, const GemmDesc& d, cudaStream_t st) {
   if (d.M <= 0 || d.N <= 0) return DCS_OK;
-  DCS_REQUIRE(d.K > 0 && d.m_inner > 0 && d.k_seg > 0 && d.cm_inner > 0 && d.n_seg > 0, "bad GEMM descriptor");
+  DCS_REQUIRE(d.K > 0 && d.m_inner > 0 && d.m_inner2 > 0 && d.k_seg > 0 && d.cm_inner > 0 && d.cm_inner2 > 0 && d.n_seg > 0, "bad GEMM descriptor");
   dim3 grid((unsigned)ceil_div64(d.N, BN), (unsigned)ceil_div64(d.M, BM));
   DCS_REQUIRE(grid.y <= 65535u * 16u, "GEMM M=%d too large", d.M);
   if (grid.y > 65535u) {
     // split M (keeps the kernel simple; only enormous clips get here)
     GemmDesc lo = d, hi = d;
     const int half = (int)((int64_t)(grid.y / 2) * BM);
-    DCS_REQUIRE(d.m_inner == 1 && d.cm_inner == 1, "GEMM M=%d too large for segmented rows", d.M);
+    DCS_REQUIRE(d.m_inner == 1 && d.cm_inner == 1 && d.m_inner2 == 1 && d.cm_inner2 == 1, "GEMM M=%d too large for segmented rows", d.M);
     lo.M = half; if (lo.a_valid_rows > half) lo.a_valid_rows = half;
     hi.M = d.M - half; hi.A = d.A + (int64_t)half * d.a_so; hi.C = d.C + (int64_t)half * d.c_so;
     hi.a_valid_rows = d.a_valid_rows - half;

@@ -51,7 +51,7 @@ gemm_tc_kernel(const GemmDesc d, const float* __restrict__ Bhi, const float* __r
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
   int kb_lo = 0, kb_hi = (d.K + KSTAGE - 1) / KSTAGE;
   if (d.kc_rows > 0) {
     const int u_min = m0 / d.kc_rows, u_max = min(d.M - 1, m0 + TC_BM - 1) / d.kc_rows;
@@ -100,8 +100,9 @@ gemm_tc_kernel(const GemmDesc d, const float* __restrict__ Bhi, const float* __r
       const int m = m0 + warp * 32 + i * RPI + sub;
       row_ok[i] = (m < d.M) && (m < d.a_valid_rows);
       const int mc = m < d.M ? m : 0;
-      arow[i] = d.A + (int64_t)(mc / d.m_inner) * d.a_so + (int64_t)(mc % d.m_inner) * d.a_si;
+      arow[i] = d.A + (int64_t)(mc / d.m_inner) * d.a_so + (int64_t)((mc % d.m_inner) / d.m_inner2) * d.a_si + (int64_t)(mc % d.m_inner2) * d.a_s2;
     }
+    const bool seg_vec = d.k_seg < d.K;   // only reached with AVEC > 1 when k_seg % KSTAGE == 0 (launcher)
     constexpr int NBI = (2 * BN) / 16;   // B: 2*BN rows (hi+lo planes), 16 rows per pass of 128 threads
     float ra[NI][AVEC];
     float4 rb[NBI];
@@ -109,14 +110,17 @@ gemm_tc_kernel(const GemmDesc d, const float* __restrict__ Bhi, const float* __r
 #pragma unroll
       for (int i = 0; i < NI; ++i) {
         const int k = (kb_lo + kb) * KSTAGE + piece * AVEC;
+        // K split in segments (one per convolution tap): with k_seg a multiple of the 32-wide
+        // stage a vector never straddles two segments
+        const int64_t koff = seg_vec ? (int64_t)(k / d.k_seg) * d.k_ss + (k % d.k_seg) : (int64_t)k;
 #pragma unroll
         for (int e = 0; e < AVEC; ++e) ra[i][e] = 0.f;
         if (row_ok[i] && k < d.K) {
           if (AVEC == 4 && k + 4 <= d.K) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(arow[i] + k));
+            const float4 v = __ldg(reinterpret_cast<const float4*>(arow[i] + koff));
             ra[i][0] = v.x; ra[i][1] = v.y; ra[i][AVEC > 2 ? 2 : 0] = v.z; ra[i][AVEC > 3 ? 3 : 0] = v.w;
           } else if (AVEC == 2 && k + 2 <= d.K) {
-            const float2 v = __ldg(reinterpret_cast<const float2*>(arow[i] + k));
+            const float2 v = __ldg(reinterpret_cast<const float2*>(arow[i] + koff));
             ra[i][0] = v.x; ra[i][AVEC > 1 ? 1 : 0] = v.y;
           } else {
 #pragma unroll
@@ -178,7 +182,7 @@ gemm_tc_kernel(const GemmDesc d, const float* __restrict__ Bhi, const float* __r
     mbar_wait(tmem_full, 0);
     fence_after_sync();
     const bool m_ok = m < d.M;
-    const int64_t roff = (int64_t)(mc / d.cm_inner) * d.c_so + (int64_t)(mc % d.cm_inner) * d.c_si + d.c_col0;
+    const int64_t roff = (int64_t)(mc / d.cm_inner) * d.c_so + (int64_t)((mc % d.cm_inner) / d.cm_inner2) * d.c_si + (int64_t)(mc % d.cm_inner2) * d.c_s2 + d.c_col0;
     const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
     for (int j = 0; j < BN / 16; ++j) {
@@ -283,7 +287,7 @@ static int launch_tc(dcs_ctx* ctx, const GemmDesc& d, const TcWeight& w, cudaStr
     DCS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, AVEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
     attr = true;
   }
-  dim3 grid((unsigned)ceil_div64(d.N, BN), (unsigned)ceil_div64(d.M, TC_BM));
+  dim3 grid((unsigned)ceil_div64(d.M, TC_BM), (unsigned)ceil_div64(d.N, BN));
   gemm_tc_kernel<BN, STAGES, AVEC><<<grid, TC_THREADS, SM::TOTAL, st>>>(d, w.hi, w.lo, w.Kp, ctx->tc_acc_mode);
   DCS_CHECK_LAUNCH();
   ctx->launches++;
@@ -294,12 +298,13 @@ static int launch_tc(dcs_ctx* ctx, const GemmDesc& d, const TcWeight& w, cudaStr
 int launch_gemm_tc(dcs_ctx* ctx, const GemmDesc& d, const TcWeight& w, cudaStream_t st) {
   if (d.M <= 0 || d.N <= 0) return DCS_OK;
   DCS_REQUIRE(d.K == w.K && d.N == w.N, "tc gemm: weight is %dx%d, GEMM wants K=%d N=%d", w.K, w.N, d.K, d.N);
-  DCS_REQUIRE(ceil_div64(d.M, TC_BM) <= 65535, "tc gemm: M=%d too large", d.M);
+  DCS_REQUIRE(ceil_div64(d.N, 64) <= 65535, "tc gemm: N=%d too large", d.N);
   // vector width the A view allows: every row start and every segment must keep the alignment
   int avec = 1;
   const bool one_seg = d.k_seg >= d.K;
   auto aligned = [&](int v) {
-    return ((uintptr_t)d.A % (4 * v) == 0) && d.a_so % v == 0 && d.a_si % v == 0 && (one_seg || (d.k_seg % v == 0 && d.k_ss % v == 0 && false));
+    return ((uintptr_t)d.A % (4 * v) == 0) && d.a_so % v == 0 && d.a_si % v == 0 && d.a_s2 % v == 0 &&
+           (one_seg || (d.k_seg % KSTAGE == 0 && d.k_ss % v == 0));
   };
   if (aligned(4)) avec = 4; else if (aligned(2)) avec = 2;
   if (d.N > 64) {

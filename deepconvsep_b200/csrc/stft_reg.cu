@@ -80,7 +80,7 @@ stft_reg_kernel(const float* __restrict__ audio, int64_t L, int hop, const float
 }
 
 template <int T, int HS>  // HS = hop / 64: window slots (32 float2 each) per hop
-__global__ void __launch_bounds__(REG_THREADS)
+__global__ void __launch_bounds__(REG_THREADS, 3)
 istft_reg_kernel(const float2* __restrict__ S, int64_t nframes, int64_t ldf, int64_t src_stride,
                  const float* __restrict__ wsyn, const float* __restrict__ w2, const float2* __restrict__ tw,
                  float* __restrict__ out, int64_t Lout, int64_t out_stride, int hops_per_group, int64_t num_hops,

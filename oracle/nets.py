@@ -188,12 +188,17 @@ def predict(params, x, arch, return_pre=False):
     return pre if return_pre else relu(pre)                              # + rectify
 
 
-def near_kink(pre, rule, nsrc, tau=2e-8):
+def near_kink(pre, rule, nsrc, tau=None):
     """Bins where the reference's soft mask is DISCONTINUOUS and the float64 value sits within
     `tau` of the jump: all rectified outputs vanish on one side ('dsd' rule: masks jump from
     (1/nsrc, ...) to (1, 0, ...); 'bach10' rule: from 0 to 1).  No finite-precision evaluation
-    can be expected to land on the oracle's side there."""
-    s = np.sort(pre[:, :nsrc], axis=1)
+    can be expected to land on the oracle's side there.  Default tau = 1e-5 x the mean absolute
+    pre-activation (>= 2e-8): a chain of six fp32-accurate contractions reproduces a
+    pre-activation to a few 1e-6 of its typical magnitude, not of its own (near-zero) value."""
+    x = pre[:, :nsrc]
+    if tau is None:
+        tau = max(2e-8, 1e-5 * float(np.mean(np.abs(x))))
+    s = np.sort(x, axis=1)
     top, second = s[:, -1], s[:, -2]
     return (np.abs(top) < tau) & (second <= tau)
 

@@ -1,0 +1,84 @@
+"""GPU parity of the strided-conv1 networks -- Bach10 (examples/bach10/separate_bach10.py) and iKala
+(examples/ikala/separate_ikala.py, pooled; ikala/trainCNN.py, un-pooled) -- against the float64 oracle.
+Same tolerance policy as tests/test_gpu_dsd.py: 1e-4 relative L2 per stem, plus the oracle's own
+worst-case bound for bins it flags as sitting on the mask discontinuity."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import dsp, nets, pipeline  # noqa: E402
+
+TOL = 1e-4
+
+
+def rel(a, b):
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def run_case(arch, F, N, hop, win_name, win_fn, overlap, seconds, patcher="standalone", seed=5, silence=None):
+    from deepconvsep_b200.engine import Separator
+    params = nets.make_synthetic_params(arch, F, seed=seed)
+    mix, _ = pipeline.synth_mixture(seconds, 70 + F)
+    if silence:
+        mix[silence[0]:silence[1]] = 0.0      # exact zeros: constant conv1 output -> max-pool ties everywhere
+    want = pipeline.separate(mix, params, arch, frameSize=N, hopSize=hop, window=win_fn, overlap=overlap,
+                             patcher=patcher, count_kinks=True)
+    kinks, bound = pipeline.separate.last_kinks, pipeline.separate.last_kink_bound
+    sep = Separator(params, arch=arch, frame_size=N, hop=hop, window=win_name, overlap=overlap, patcher=patcher,
+                    feat_size=F)
+    got = sep.separate(mix)
+    assert got.shape == want.shape
+    assert min(np.linalg.norm(w) for w in want) > 0.02 * np.linalg.norm(mix)
+    for s in range(want.shape[0]):
+        e = rel(got[s].astype(np.float64), want[s])
+        allow = TOL if not kinks else TOL + 1.5 * bound[s]
+        assert e <= allow, (arch, s, e, allow, kinks)
+    return sep
+
+
+@pytest.mark.parametrize("F,N,hop,seconds,patcher", [(129, 256, 128, 1.0, "standalone"), (257, 512, 256, 1.5, "util"),
+                                                     (129, 256, 128, 0.4, "util")])
+def test_bach10_small(F, N, hop, seconds, patcher):
+    run_case("bach10", F, N, hop, "blackmanharris", dsp.blackmanharris, 25, seconds, patcher)
+
+
+def test_ikala_pooled_with_silence():
+    sep = run_case("ikala", 513, 1024, 512, "hanning", np.hanning, 20, 3.0, silence=(20000, 40000))
+    assert sep.nsrc == 2 and sep.sources == ["voice", "music"]
+
+
+def test_ikala_nopool():
+    run_case("ikala_nopool", 513, 1024, 512, "hanning", np.hanning, 20, 1.2, seed=9)
+
+
+def test_bach10_full_size():
+    """The real configuration: N=4096, F=2049, 214 M parameters (856 MB), one second of audio."""
+    run_case("bach10", 2049, 4096, 512, "blackmanharris", dsp.blackmanharris, 25, 1.0, seed=2)
+
+
+def test_models_share_a_context_safely():
+    """DSD100 and Bach10 alternating on ONE ctx: the zero-padded workspaces are re-zeroed when the layout changes."""
+    from deepconvsep_b200.engine import Context, Model, Stft
+    from deepconvsep_b200 import _lib
+    import ctypes as C
+    ctx = Context(0)
+    lib = ctx.lib
+    mix, _ = pipeline.synth_mixture(1.0, 3)
+    outs = {}
+    for rnd in range(2):
+        for arch, F, N, hop, win, ov in (("dsd", 257, 512, 256, np.hanning, 25), ("bach10", 257, 512, 256, dsp.blackmanharris, 25)):
+            params = nets.make_synthetic_params(arch, F, seed=4)
+            model = Model(ctx, params, arch=arch, feat_size=F)
+            st = Stft(ctx, N, hop, win(N))
+            a = np.ascontiguousarray(mix, dtype=np.float32)
+            out = np.empty((4, a.size), dtype=np.float32)
+            _lib.check(lib.dcs_separate_host(ctx.handle, model.handle, st.handle, a.ctypes.data, a.size, C.c_float(0.3), ov, 0,
+                                             out.ctypes.data, a.size, None))
+            if rnd == 0:
+                outs[arch] = out
+                want = pipeline.separate(mix, params, arch, frameSize=N, hopSize=hop, window=win, overlap=ov)
+                assert max(rel(out[s].astype(np.float64), want[s]) for s in range(4)) < 5e-4
+            else:
+                assert np.array_equal(out, outs[arch])
