@@ -340,45 +340,58 @@ def run_ours(args):
     workers = [sep] + [Separator(params, frame_size=N, hop=512, window="hanning", overlap=25, device=local)
                        for _ in range(ns - 1)]
     streams = [torch.cuda.Stream(device=dev) for _ in range(ns)]
+    # (a) the wav contract of train_auto (separate_dsd.py:275-287,307-309): int16 samples in, int16 stems out
+    # (b) float32 host buffers (dcs_separate_host)
+    h_in16 = [torch.empty(L, dtype=torch.int16).pin_memory() for _ in range(B)]
+    h_out16 = [torch.empty((4, L), dtype=torch.int16).pin_memory() for _ in range(B)]
     h_in = [torch.empty(L, dtype=torch.float32).pin_memory() for _ in range(B)]
     h_out = [torch.empty((4, L), dtype=torch.float32).pin_memory() for _ in range(B)]
     for i in range(B):
         h_in[i].copy_(clips[i].cpu())
-    np_in = [t.numpy() for t in h_in]
-    np_out = [t.numpy() for t in h_out]
+        h_in16[i].copy_(torch.round(clips[i].cpu() * 32767).to(torch.int16))
+    np_in, np_out = [t.numpy() for t in h_in], [t.numpy() for t in h_out]
+    np_in16, np_out16 = [t.numpy() for t in h_in16], [t.numpy() for t in h_out16]
 
-    def e2e_worker(w, nsteps):
+    def e2e_worker(w, nsteps, pcm):
         torch.cuda.set_device(local)
         with torch.cuda.stream(streams[w]):
             for _ in range(nsteps):
                 for i in range(w, B, ns):
-                    workers[w].separate(np_in[i], out=np_out[i])
+                    if pcm:
+                        workers[w].separate_pcm16(np_in16[i], out=np_out16[i])
+                    else:
+                        workers[w].separate(np_in[i], out=np_out[i])
 
-    def e2e_run(nsteps):
-        ths = [threading.Thread(target=e2e_worker, args=(w, nsteps)) for w in range(ns)]
+    def e2e_run(nsteps, pcm):
+        ths = [threading.Thread(target=e2e_worker, args=(w, nsteps, pcm)) for w in range(ns)]
         for t in ths:
             t.start()
         for t in ths:
             t.join()
 
-    e2e_run(2)
-    barrier()
-    l0 = sum(w.ctx.launch_count() for w in workers)
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    e2e_run(K)
-    for s in streams:
-        torch.cuda.current_stream().wait_stream(s)
-    f1.record()
-    barrier()
-    e2e_launches = sum(w.ctx.launch_count() for w in workers) - l0
-    ems = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ems, op=dist.ReduceOp.MAX)
-    ems = float(ems.item())
+    def e2e_measure(pcm):
+        e2e_run(2, pcm)
+        barrier()
+        l0 = sum(w.ctx.launch_count() for w in workers)
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        e2e_run(K, pcm)
+        for s in streams:
+            torch.cuda.current_stream().wait_stream(s)
+        f1.record()
+        barrier()
+        nl = sum(w.ctx.launch_count() for w in workers) - l0
+        t = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), nl
+
+    ems_f32, _ = e2e_measure(False)
+    ems, e2e_launches = e2e_measure(True)
     e2e_value = audio_s / (ems * 1e-3)
-    # result check on the host copy: the four stems add up to the mixture where masks cover it
+    # result checks on the host copies: the four stems add up to the mixture where masks cover it
     chk = float(np.abs(np_out[0][:, 44100:88200].sum(0) - np_in[0][44100:88200]).max())
+    chk16 = int(np.abs(np_out16[0][:, 44100:88200].astype(np.int32).sum(0) - np_in16[0][44100:88200]).max())
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle on a bounded sample --------------------
     cpu = None
@@ -397,9 +410,13 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic", "config": workload_config(args),
             "x_realtime": value, "gpu_launches": int(launches), "outputs_finite": finite,
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * L * 4, "d2h_bytes_per_step": B * 4 * L * 4,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * L * 2, "d2h_bytes_per_step": B * 4 * L * 2,
                     "ms_per_step": ems / K, "streams": ns, "gpu_launches": int(e2e_launches),
-                    "api": "dcs_separate_host (pinned float32 host buffers)", "stem_sum_max_abs_err": chk},
+                    "api": "dcs_separate_pcm16_host: pinned int16 wav samples in, int16 stems out (train_auto's wav contract)",
+                    "stem_sum_max_abs_err_lsb": chk16,
+                    "float32_buffers": {"value": audio_s / (ems_f32 * 1e-3), "ms_per_step": ems_f32 / K,
+                                        "h2d_bytes_per_step": B * L * 4, "d2h_bytes_per_step": B * 4 * L * 4,
+                                        "api": "dcs_separate_host", "stem_sum_max_abs_err": chk}},
             "roofline": roofline, "stages": stage_table, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

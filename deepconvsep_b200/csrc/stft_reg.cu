@@ -100,6 +100,22 @@ istft_reg_kernel(const float2* __restrict__ S, int64_t nframes, int64_t ldf, int
 #pragma unroll
   for (int i = 0; i < 32; ++i) acc[i] = make_float2(0.f, 0.f);
   float* o = out + (int64_t)src * out_stride;
+  // 1 / sum_r win*syn_win for the interior of the clip (every hop sees the same R frames)
+  float2 cinv[G::Q * HS];
+#pragma unroll
+  for (int q = 0; q < G::Q; ++q)
+#pragma unroll
+    for (int kb = 0; kb < HS; ++kb) {
+      const int e = 2 * ((b + T * q) + 32 * kb);
+      float c0 = 0.f, c1 = 0.f;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float2 ww = __ldg(reinterpret_cast<const float2*>(w2 + e + r * hop));
+        c0 += ww.x;
+        c1 += ww.y;
+      }
+      cinv[q * HS + kb] = make_float2(c0 == 0.f ? 1.f : 1.f / c0, c1 == 0.f ? 1.f : 1.f / c1);
+    }
 
   for (int64_t n = h0 + C0 - R + 1; n <= h0 + hops_per_group - 1 + C0; ++n) {
     const bool fvalid = n >= 0 && n < nframes;
@@ -131,29 +147,32 @@ istft_reg_kernel(const float2* __restrict__ S, int64_t nframes, int64_t ldf, int
     // the oldest hop of the window is complete: padded samples [n*hop, (n+1)*hop) -> output hop n - C0
     const int64_t h = n - C0;
     if (active && h >= h0 && h < num_hops) {
+      const bool interior = (n - (R - 1) >= 0) && (n < nframes);   // all R overlapping frames exist
 #pragma unroll
       for (int q = 0; q < G::Q; ++q)
 #pragma unroll
         for (int kb = 0; kb < HS; ++kb) {
           const int e = 2 * ((b + T * q) + 32 * kb);  // sample offset inside the hop
-          float c0 = 0.f, c1 = 0.f;                   // sum of win*syn_win over the frames covering it
+          float2 ic = cinv[q * HS + kb];
+          if (!interior) {   // clip edges: sum win*syn_win over the frames that exist (transform.py:384-392)
+            float c0 = 0.f, c1 = 0.f;
 #pragma unroll
-          for (int r = 0; r < R; ++r) {
-            const int64_t nf = n - r;
-            if (nf >= 0 && nf < nframes) {
-              const float2 ww = __ldg(reinterpret_cast<const float2*>(w2 + e + r * hop));
-              c0 += ww.x;
-              c1 += ww.y;
+            for (int r = 0; r < R; ++r) {
+              const int64_t nf = n - r;
+              if (nf >= 0 && nf < nframes) {
+                const float2 ww = __ldg(reinterpret_cast<const float2*>(w2 + e + r * hop));
+                c0 += ww.x;
+                c1 += ww.y;
+              }
             }
+            ic = make_float2(c0 == 0.f ? 1.f : 1.f / c0, c1 == 0.f ? 1.f : 1.f / c1);
           }
-          if (c0 == 0.f) c0 = 1.f;  // transform.py:392
-          if (c1 == 0.f) c1 = 1.f;
           const int64_t oi = h * hop + e;
           const float2 a2 = acc[q * T + kb];
           if (oi + 1 < Lout) {
-            *reinterpret_cast<float2*>(o + oi) = make_float2(a2.x / c0, a2.y / c1);
+            *reinterpret_cast<float2*>(o + oi) = make_float2(a2.x * ic.x, a2.y * ic.y);
           } else if (oi < Lout) {
-            o[oi] = a2.x / c0;
+            o[oi] = a2.x * ic.x;
           }
         }
     }
