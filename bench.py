@@ -8,8 +8,9 @@ One "step" = one pass of the hot path (STFT -> encoder/decoder -> soft mask + cr
 iSTFT/OLA) over one batch of `--clips` synthetic 180 s mono 44.1 kHz mixtures per GPU
 (BASELINE.json configs[1]: frameSize=2048, hop=512, time_context=30, overlap 25, 4 sources).
 `value`   : whole-job audio-s/s with the inputs already resident in HBM (CUDA events, max over ranks);
-`e2e`     : the same metric through the C-ABI host-buffer call (pinned host float32 in, H2D,
-            pipeline, D2H of the 4 stems) -- what a user of the drop-in API gets;
+`e2e`     : the same metric through the C-ABI host-buffer call with pinned host memory, H2D and D2H
+            inside the timed region: int16 wav samples in / int16 stems out (train_auto's contract,
+            dcs_separate_pcm16_host); the float32-buffer call (dcs_separate_host) is reported beside it;
 `roofline`: dominant kernel, timed live with CUDA events on its own stream (dcs_profile);
 `cpu_baseline`: the float64 numpy oracle (the restated reference path) on a bounded sample.
 `--impl reference` times that CPU path on all host cores (the reference itself -- Python 2 +
@@ -30,6 +31,7 @@ if ROOT not in sys.path:
 
 SR = 44100
 METRIC = "audio_seconds_separated_per_second"
+_emit = print
 UNIT = "audio-s/s"
 
 
@@ -235,7 +237,7 @@ def run_reference(args):
         "note": "the reference's own runtime (Python 2.7 + Theano 0.9 + Lasagne) is not installable here; this is "
                 "the oracle port of its CPU path",
     }
-    print(json.dumps(line), flush=True)
+    _emit(json.dumps(line))
 
 
 def workload_config(args, cpu=False):
@@ -419,7 +421,7 @@ def run_ours(args):
                                         "api": "dcs_separate_host", "stem_sum_max_abs_err": chk}},
             "roofline": roofline, "stages": stage_table, "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        _emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -436,6 +438,15 @@ def _cpu_worker_threads(seconds, N):
 
 def main():
     args = parse_args()
+    # stdout must carry exactly ONE JSON line: NCCL / torchrun / libraries print banners to fd 1
+    # ("NCCL version ..."), so everything else is sent to stderr and the line is written to the
+    # original descriptor at the end.
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    out = os.fdopen(real, "w")
+    global _emit
+    _emit = lambda line: (out.write(line + "\n"), out.flush())
     if args.impl == "reference":
         run_reference(args)
     else:
