@@ -143,7 +143,7 @@ dsd_mask_tc_kernel(const DsdMaskArgs a, int groups_per_cta, int num_groups) {
     for (int g = g_begin; g < g_end; ++g) {
       const int it = g - g_begin, s = it & 1;
       if (g + 1 < g_end) build_table(g + 1, row_src + ((it + 1) & 1) * MT_COLS);
-      mbar_wait(&empty_b[s], ((it >> 1) & 1) ^ 1);
+      mbar_wait_relaxed(&empty_b[s], ((it >> 1) & 1) ^ 1);
       uint8_t* st = sB + s * MT_B_STAGE;
 #pragma unroll
       for (int u = 0; u < CPT; ++u) {
@@ -215,7 +215,7 @@ dsd_mask_tc_kernel(const DsdMaskArgs a, int groups_per_cta, int num_groups) {
         klo[ff] = k_lo;
         np[ff] = t < a.T ? k_hi - k_lo + 1 : 0;   // <= 6 (checked by the launcher)
       }
-      mbar_wait(&tmem_full[s], (it >> 1) & 1);
+      mbar_wait_relaxed(&tmem_full[s], (it >> 1) & 1);
       fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + s * 256 + 36 * fsub;
       float y[2][18];

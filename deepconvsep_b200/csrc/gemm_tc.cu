@@ -143,7 +143,7 @@ gemm_tc_kernel(const GemmDesc d, const float* __restrict__ Bhi, const float* __r
     for (int kb = pg; kb < num_kb; kb += TC_PGROUPS) {
       const int s = kb % STAGES;
       const uint32_t par = (kb / STAGES) & 1;
-      mbar_wait(&empty[s], par ^ 1);
+      mbar_wait_relaxed(&empty[s], par ^ 1);
       uint8_t* st = smem + s * SM::STAGE_BYTES;
 #pragma unroll
       for (int i = 0; i < NI; ++i) {
@@ -179,7 +179,7 @@ gemm_tc_kernel(const GemmDesc d, const float* __restrict__ Bhi, const float* __r
     const int m = m0 + r;
     const int mc = m < d.M ? m : 0;
     // ------------------------------------------------------------------ epilogue
-    mbar_wait(tmem_full, 0);
+    mbar_wait_relaxed(tmem_full, 0);
     fence_after_sync();
     const bool m_ok = m < d.M;
     const int64_t roff = (int64_t)(mc / d.cm_inner) * d.c_so + (int64_t)((mc % d.cm_inner) / d.cm_inner2) * d.c_si + (int64_t)(mc % d.cm_inner2) * d.c_s2 + d.c_col0;

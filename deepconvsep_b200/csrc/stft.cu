@@ -232,7 +232,8 @@ int launch_istft(dcs_stft* p, const float2* d_S, const float* d_mag, const float
                  int64_t out_stride, cudaStream_t st) {
   DCS_REQUIRE(Lout <= (T - 1) * p->hop + p->N - p->N / 2, "num_out %lld exceeds the istft length", (long long)Lout);
   if (Lout <= 0 || nsrc <= 0) return DCS_OK;
-  if (d_S && istft_reg_supported(p, d_out, out_stride) && !p->ctx->debug_smem_fft)
+  if (d_S && istft_reg_supported(p, d_out, out_stride) && !p->ctx->debug_smem_fft && ldf % 2 == 0 &&
+      src_stride % 2 == 0 && ((uintptr_t)d_S % 16 == 0) && ldf >= (p->N / 2 + 2) / 2 * 2)
     return launch_istft_reg(p, d_S, nsrc, T, ldf, src_stride, d_out, Lout, out_stride, st);
 #define DCS_ISTFT_CASE(NN) \
   case NN: return launch_istft_n<NN>(p, d_S, d_mag, d_phase, polar_scale, nsrc, T, ldf, src_stride, d_out, Lout, out_stride, st);

@@ -117,21 +117,41 @@ istft_reg_kernel(const float2* __restrict__ S, int64_t nframes, int64_t ldf, int
       cinv[q * HS + kb] = make_float2(c0 == 0.f ? 1.f : 1.f / c0, c1 == 0.f ? 1.f : 1.f / c1);
     }
 
-  for (int64_t n = h0 + C0 - R + 1; n <= h0 + hops_per_group - 1 + C0; ++n) {
+  // The spectrum row of the NEXT frame is fetched into shared memory with cp.async while the
+  // current frame is transformed and overlap-added: HBM latency is off the critical path.
+  constexpr int ROWP = (N2 + 1 + 7) / 8 * 8;          // float2 per staged row
+  constexpr int CHUNKS = (N2 + 2) / 2;                // 16-byte pieces covering bins 0..N2
+  float2* srow = scratch + GPC * G::SCRATCH + gl * ROWP;
+  auto prefetch = [&](int64_t nn) {
+    if (nn >= 0 && nn < nframes) {
+      const float2* rowp = S + (int64_t)src * src_stride + nn * ldf;
+      for (int c = b; c < CHUNKS; c += T) {
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(srow + 2 * c);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(rowp + 2 * c) : "memory");
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  const int64_t n_first = h0 + C0 - R + 1, n_last = h0 + hops_per_group - 1 + C0;
+  prefetch(n_first);
+  for (int64_t n = n_first; n <= n_last; ++n) {
     const bool fvalid = n >= 0 && n < nframes;
-    const int64_t row = (int64_t)src * src_stride + (fvalid ? n : 0) * ldf;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
     float2 v[32];
 #pragma unroll
     for (int a = 0; a < 32; ++a) {
       const int idx = a * T + b;
       float2 xk = make_float2(0.f, 0.f), xn = xk;
       if (fvalid) {
-        xk = S[row + idx];
-        xn = S[row + N2 - idx];
+        xk = srow[idx];
+        xn = srow[N2 - idx];
       }
       if (idx == 0) { xk.y = 0.f; xn.y = 0.f; }  // irfft ignores Im of DC and Nyquist
       v[a] = real_pre_conj(xk, xn, __ldg(tw + idx));
     }
+    __syncwarp();                    // every lane has consumed the row
+    if (n < n_last) prefetch(n + 1);
     G::forward(v, scr, tw, b);
     // z = conj(V)/N2: samples 2n', 2n'+1 of the frame, n' = (b + T q) + 32 kb  <->  v[q*T + kb]
 #pragma unroll
@@ -212,6 +232,7 @@ int launch_stft_reg(dcs_stft* p, const float* d_audio, int64_t L, float2* d_X, f
 }
 
 bool istft_reg_supported(const dcs_stft* p, const float* d_out, int64_t out_stride) {
+  // (the caller also guarantees 16-byte aligned spectrum rows: ldf % 2 == 0, see launch_istft)
   return (p->N == 1024 || p->N == 2048) && (p->hop == 512 || p->hop == 256) && ((uintptr_t)d_out % 8 == 0) &&
          out_stride % 2 == 0;
 }
@@ -232,7 +253,14 @@ static int launch_istft_reg_t(dcs_stft* p, const float2* d_S, int nsrc, int64_t 
   const int64_t groups_per_src = ceil_div64(num_hops, hpg);
   const int64_t total = groups_per_src * nsrc;
   const unsigned grid = (unsigned)ceil_div64(total, GPC);
-  istft_reg_kernel<T, HS><<<grid, REG_THREADS, GPC * G::SCRATCH * sizeof(float2), st>>>(
+  constexpr int ROWP = (G::N2 + 1 + 7) / 8 * 8;
+  const size_t smem = (size_t)GPC * (G::SCRATCH + ROWP) * sizeof(float2);
+  static bool attr = false;
+  if (!attr) {
+    DCS_CUDA(cudaFuncSetAttribute(istft_reg_kernel<T, HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  istft_reg_kernel<T, HS><<<grid, REG_THREADS, smem, st>>>(
       d_S, nframes, ldf, src_stride, p->d_wsyn, p->d_w2, p->d_tw, d_out, Lout, out_stride, (int)hpg, num_hops,
       groups_per_src, total);
   DCS_CHECK_LAUNCH();

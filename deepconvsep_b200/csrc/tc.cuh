@@ -48,6 +48,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// same, for waits that are expected to be long (epilogue waiting for a whole tile, producers waiting
+// for a stage): back off between polls so the spinning warps do not steal issue slots from the
+// warps doing the work
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "DCS_WAITR:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DCS_DONER;\n\t"
+      "nanosleep.u32 64;\n\t"
+      "bra DCS_WAITR;\n\t"
+      "DCS_DONER:\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
 // generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
