@@ -87,6 +87,8 @@ int dcs_create(int device, dcs_ctx** out) {
   c->num_sms = prop.multiProcessorCount;
   const char* dbg = getenv("DCS_DEBUG_SIMT_GEMM");
   c->debug_simt_gemm = dbg && dbg[0] == '1';
+  const char* sk = getenv("DCS_DEBUG_TC_SKIP");
+  if (sk && sk[0] >= '0' && sk[0] <= '7') c->tc_debug = sk[0] - '0';
   const char* sf = getenv("DCS_DEBUG_SMEM_FFT");
   c->debug_smem_fft = sf && sf[0] == '1';
   const char* am = getenv("DCS_DEBUG_TC_ACC");

@@ -62,6 +62,7 @@ struct dcs_ctx {
   bool prof_on = false;
   bool debug_simt_gemm = false;
   int tc_acc_mode = 2;
+  int tc_debug = 0;
   bool debug_smem_fft = false;
   std::vector<dcs_prof_rec> prof;
   // workspace of one in-flight pipeline

@@ -41,7 +41,8 @@ constexpr int MT_A_BYTES = 4 * MT_A_SUB;           // hi k0-31, hi k32-63, lo k0
 constexpr int MT_B_STAGE = 4 * MT_B_SUB;           // same four planes
 constexpr int MT_BAR_OFF = MT_A_BYTES + 2 * MT_B_STAGE;
 constexpr int MT_TAB_OFF = MT_BAR_OFF + 128;       // int64 source-row offsets of the 144 B rows
-constexpr int MT_SMEM = MT_TAB_OFF + 2 * MT_COLS * 8 + 1024;  // two row tables + alignment slack
+constexpr int MT_XF_OFF = MT_TAB_OFF + 2 * MT_COLS * 8;   // cross-fade coefficient tables, 12 float4 per epilogue warp
+constexpr int MT_SMEM = MT_XF_OFF + MT_EPI_WARPS * 12 * 16 + 1024;  // + alignment slack
 constexpr uint32_t MT_TMEM_COLS = 512;
 
 __global__ void __launch_bounds__(MT_THREADS, 1)
@@ -199,22 +200,34 @@ dsd_mask_tc_kernel(const DsdMaskArgs a, int groups_per_cta, int num_groups) {
     const bool bok = b < a.F;
     const float bo0 = __ldg(a.bout + 0), bo1 = __ldg(a.bout + 1), bo2 = __ldg(a.bout + 2), bo3 = __ldg(a.bout + 3);
     const float inv_ov1 = a.overlap > 1 ? 1.0f / (float)(a.overlap - 1) : 0.f;
+    float4* xf = reinterpret_cast<float4*>(smem + MT_XF_OFF) + warp * 12;
     for (int g = g_begin; g < g_end; ++g) {
       const int it = g - g_begin, s = it & 1;
       const int tA = g * MT_FRAMES + 2 * fsub;
-      float2 xs[2];
-      int np[2], klo[2];
-#pragma unroll
-      for (int ff = 0; ff < 2; ++ff) {
-        const int t = tA + ff;
-        xs[ff] = (bok && t < a.T) ? a.X[(int64_t)t * a.ldf + b] : make_float2(0.f, 0.f);
+      // cross-fade coefficients of this warp's 2 frames x 6 patch slots, one per lane 0..11:
+      // acc <- down*acc + up*mask, (up, down) = (1, 0) for the first covering patch, the linspace
+      // ramp for later ones, (0, 1) for empty slots -- the evaluation below is branch free
+      if (lane < 12) {
+        const int ff = lane / 6, j = lane - 6 * ff, t = tA + ff;
         int k_lo = t - a.tc + 1;
         k_lo = k_lo > 0 ? (k_lo + step - 1) / step : 0;
         int k_hi = t / step;
         if (k_hi > a.P - 1) k_hi = a.P - 1;
-        klo[ff] = k_lo;
-        np[ff] = t < a.T ? k_hi - k_lo + 1 : 0;   // <= 6 (checked by the launcher)
+        float up = 0.f, down = 1.f;
+        if (t < a.T && k_lo + j <= k_hi) {
+          const int p = t - (k_lo + j) * step;
+          up = j == 0 ? 1.f : (float)p * inv_ov1;
+          down = j == 0 ? 0.f : (float)(a.overlap - 1 - p) * inv_ov1;
+        }
+        xf[lane] = make_float4(up, down, 0.25f * up, 0.f);
       }
+      float2 xs[2];
+#pragma unroll
+      for (int ff = 0; ff < 2; ++ff) {
+        const int t = tA + ff;
+        xs[ff] = (bok && t < a.T) ? a.X[(int64_t)t * a.ldf + b] : make_float2(0.f, 0.f);
+      }
+      __syncwarp();
       mbar_wait_relaxed(&tmem_full[s], (it >> 1) & 1);
       fence_after_sync();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + s * 256 + 36 * fsub;
@@ -234,22 +247,19 @@ dsd_mask_tc_kernel(const DsdMaskArgs a, int groups_per_cta, int num_groups) {
       for (int j = 0; j < MT_SLOTS; ++j) {
 #pragma unroll
         for (int ff = 0; ff < 2; ++ff) {
-          if (j < np[ff]) {   // warp-uniform
-            const int p = tA + ff - (klo[ff] + j) * step;
-            // first covering patch: assign (down = 0, up = 1); later ones: linear cross-fade
-            const float up = j == 0 ? 1.f : (float)p * inv_ov1;
-            const float down = j == 0 ? 0.f : (float)(a.overlap - 1 - p) * inv_ov1;
-            const float p0 = fmaxf(y[ff][3 * j + 0] + bo0, 0.f), p1 = fmaxf(y[ff][3 * j + 1] + bo1, 0.f);
-            const float p2 = fmaxf(y[ff][3 * j + 2] + bo2, 0.f), p3 = fmaxf(y[ff][3 * j + 1] + bo3, 0.f);
-            const float tot = (p0 + p1) + (p2 + p3);
-            const bool pos = tot > 0.f;
-            const float r = pos ? __fdividef(up, tot) : 0.f;  // up * mask = p * (up / tot); MUFU.RCP, 2 ulp
-            const float q = pos ? 0.f : 0.25f * up;      // all-zero bin: 1/4 each
-            acc[ff][0] = fmaf(down, acc[ff][0], fmaf(p0, r, q));
-            acc[ff][1] = fmaf(down, acc[ff][1], fmaf(p1, r, q));
-            acc[ff][2] = fmaf(down, acc[ff][2], fmaf(p2, r, q));
-            acc[ff][3] = fmaf(down, acc[ff][3], fmaf(p3, r, q));
-          }
+          const float4 c = xf[ff * 6 + j];   // (up, down, up/4, -)
+          const float p0 = fmaxf(y[ff][3 * j + 0] + bo0, 0.f), p1 = fmaxf(y[ff][3 * j + 1] + bo1, 0.f);
+          const float p2 = fmaxf(y[ff][3 * j + 2] + bo2, 0.f), p3 = fmaxf(y[ff][3 * j + 1] + bo3, 0.f);
+          const float tot = (p0 + p1) + (p2 + p3);
+          const bool pos = tot > 1.2e-38f;
+          float rc;
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(tot));
+          const float r = pos ? c.x * rc : 0.f;        // up * mask = p * (up / tot)
+          const float q = pos ? 0.f : c.z;             // all-zero bin: 1/4 each
+          acc[ff][0] = fmaf(c.y, acc[ff][0], fmaf(p0, r, q));
+          acc[ff][1] = fmaf(c.y, acc[ff][1], fmaf(p1, r, q));
+          acc[ff][2] = fmaf(c.y, acc[ff][2], fmaf(p2, r, q));
+          acc[ff][3] = fmaf(c.y, acc[ff][3], fmaf(p3, r, q));
         }
       }
 #pragma unroll
@@ -264,6 +274,7 @@ dsd_mask_tc_kernel(const DsdMaskArgs a, int groups_per_cta, int num_groups) {
           a.S[o + 3 * a.src_stride] = make_float2(acc[ff][3] * x.x, acc[ff][3] * x.y);
         }
       }
+      __syncwarp();   // xf is rewritten at the top of the next iteration
     }
   }
   fence_before_sync();

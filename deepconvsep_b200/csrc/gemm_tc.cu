@@ -41,7 +41,7 @@ struct TcSmem {
 //   acc_mode 0: one accumulator for everything; 1: main + corrections; 2: 3 x main + corrections
 template <int BN, int STAGES, int AVEC>
 __global__ void __launch_bounds__(TC_THREADS)
-gemm_tc_kernel(const GemmDesc d, const float* __restrict__ Bhi, const float* __restrict__ Blo, int Kp, int acc_mode) {
+gemm_tc_kernel(const GemmDesc d, const float* __restrict__ Bhi, const float* __restrict__ Blo, int Kp, int acc_mode, int dbg) {
   using SM = TcSmem<BN, STAGES>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
@@ -139,12 +139,14 @@ gemm_tc_kernel(const GemmDesc d, const float* __restrict__ Bhi, const float* __r
         rb[i] = ld_stream(reinterpret_cast<const float4*>(src));
       }
     };
-    if (pg < num_kb) gload(pg);
+    // bring-up probes (DCS_DEBUG_TC_SKIP): bit0 = no global loads, bit1 = no MMAs, bit2 = no shared stores
+    if (pg < num_kb && !(dbg & 1)) gload(pg);
     for (int kb = pg; kb < num_kb; kb += TC_PGROUPS) {
       const int s = kb % STAGES;
       const uint32_t par = (kb / STAGES) & 1;
       mbar_wait_relaxed(&empty[s], par ^ 1);
       uint8_t* st = smem + s * SM::STAGE_BYTES;
+      if (!(dbg & 4)) {
 #pragma unroll
       for (int i = 0; i < NI; ++i) {
         const int r = warp * 32 + i * RPI + sub;
@@ -170,9 +172,10 @@ gemm_tc_kernel(const GemmDesc d, const float* __restrict__ Bhi, const float* __r
         const int which = rr / BN, rn = rr - which * BN;
         *reinterpret_cast<float4*>(st + 2 * SM::A_BYTES + which * SM::B_BYTES + tile_off(rn, tid & 7)) = rb[i];
       }
+      }
       fence_proxy_async();
       mbar_arrive(&full[s]);
-      if (kb + TC_PGROUPS < num_kb) gload(kb + TC_PGROUPS);
+      if (kb + TC_PGROUPS < num_kb && !(dbg & 1)) gload(kb + TC_PGROUPS);
     }
     if (pg == 0) {               // epilogue: warps 0-3, thread = output row = TMEM lane
     const int r = tid;
@@ -228,6 +231,7 @@ gemm_tc_kernel(const GemmDesc d, const float* __restrict__ Bhi, const float* __r
       const uint32_t a_lo = a_hi + SM::A_BYTES;
       const uint32_t b_hi = a_hi + 2 * SM::A_BYTES;
       const uint32_t b_lo = b_hi + SM::B_BYTES;
+      if (!(dbg & 2))
 #pragma unroll
       for (int j = 0; j < KSTAGE / 8; ++j) {
         const uint64_t dah = make_desc(a_hi + KSTEP_BYTES * j), dal = make_desc(a_lo + KSTEP_BYTES * j);
@@ -288,7 +292,7 @@ static int launch_tc(dcs_ctx* ctx, const GemmDesc& d, const TcWeight& w, cudaStr
     attr = true;
   }
   dim3 grid((unsigned)ceil_div64(d.M, TC_BM), (unsigned)ceil_div64(d.N, BN));
-  gemm_tc_kernel<BN, STAGES, AVEC><<<grid, TC_THREADS, SM::TOTAL, st>>>(d, w.hi, w.lo, w.Kp, ctx->tc_acc_mode);
+  gemm_tc_kernel<BN, STAGES, AVEC><<<grid, TC_THREADS, SM::TOTAL, st>>>(d, w.hi, w.lo, w.Kp, ctx->tc_acc_mode, ctx->tc_debug);
   DCS_CHECK_LAUNCH();
   ctx->launches++;
   return DCS_OK;
