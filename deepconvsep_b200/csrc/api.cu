@@ -306,7 +306,8 @@ int dcs_model_create(dcs_ctx* ctx, int arch, int feat_size, int time_context, in
     case DCS_ARCH_DSD: r = model_create_dsd(m, nparams, h_params, shapes, ndims); break;
     case DCS_ARCH_IKALA:
     case DCS_ARCH_IKALA_NOPOOL:
-    case DCS_ARCH_BACH10: r = model_create_sconv(m, nparams, h_params, shapes, ndims); break;
+    case DCS_ARCH_BACH10:
+    case DCS_ARCH_BACH10_SCORE: r = model_create_sconv(m, nparams, h_params, shapes, ndims); break;
     default:
       set_error("dcs_model_create: architecture %d has no CUDA path yet", arch);
       r = DCS_EINVAL;
@@ -390,10 +391,48 @@ int dcs_separate_spec(dcs_ctx* ctx, dcs_model* m, const float* d_mag, const dcs_
     case DCS_ARCH_IKALA:
     case DCS_ARCH_IKALA_NOPOOL:
     case DCS_ARCH_BACH10:
-      return sconv_forward(ctx, m, d_mag, (const float2*)d_X, T, ldf, overlap, patcher, (float2*)d_S, src_stride,
+      return sconv_forward(ctx, m, d_mag, 0, (const float2*)d_X, T, ldf, overlap, patcher, (float2*)d_S, src_stride,
                            (cudaStream_t)stream);
+    case DCS_ARCH_BACH10_SCORE:
+      DCS_REQUIRE(false, "the score-informed network takes 4 input channels: use dcs_separate_spec_channels / dcs_separate_audio_score");
   }
   DCS_REQUIRE(false, "architecture %d has no CUDA path yet", m->arch);
+}
+
+int dcs_separate_spec_channels(dcs_ctx* ctx, dcs_model* m, const float* d_in, int64_t in_plane, const dcs_complex* d_X,
+                               int64_t T, int64_t ldf, int overlap, int patcher, dcs_complex* d_S, int64_t src_stride,
+                               void* stream) {
+  DCS_REQUIRE(ctx && m && d_in && d_X && d_S, "dcs_separate_spec_channels: NULL argument");
+  DCS_REQUIRE(m->arch == DCS_ARCH_BACH10_SCORE, "dcs_separate_spec_channels: architecture %d has a single input channel", m->arch);
+  DCS_REQUIRE(T > 0 && ldf >= m->F && src_stride >= T * ldf && in_plane >= T * ldf, "dcs_separate_spec_channels: bad shape");
+  DCS_REQUIRE(overlap >= 0 && overlap < m->tc, "overlap %d must be in [0, time_context=%d)", overlap, m->tc);
+  DCS_REQUIRE(patcher == DCS_PATCHER_STANDALONE || patcher == DCS_PATCHER_UTIL, "unknown patcher %d", patcher);
+  DCS_CUDA(cudaSetDevice(ctx->device));
+  return sconv_forward(ctx, m, d_in, in_plane, (const float2*)d_X, T, ldf, overlap, patcher, (float2*)d_S, src_stride,
+                       (cudaStream_t)stream);
+}
+
+int dcs_separate_audio_score(dcs_ctx* ctx, dcs_model* m, dcs_stft* p, const float* d_audio, int64_t L, const float* d_filters,
+                             float scale_factor, int overlap, int patcher, float* d_stems, int64_t stem_stride, void* stream) {
+  DCS_REQUIRE(ctx && m && p && d_audio && d_filters && d_stems, "dcs_separate_audio_score: NULL argument");
+  DCS_REQUIRE(m->arch == DCS_ARCH_BACH10_SCORE, "dcs_separate_audio_score: needs the score-informed architecture");
+  DCS_REQUIRE(L > 0 && stem_stride >= L && p->N / 2 + 1 == m->F, "dcs_separate_audio_score: bad length / frame size");
+  cudaStream_t st = (cudaStream_t)stream;
+  DCS_CUDA(cudaSetDevice(ctx->device));
+  const int64_t T = dcs_num_frames(L, p->hop), ldf = dcs_padded_bins(p->N), plane = T * ldf;
+  DCS_TRY(ctx->X.ensure((size_t)plane * sizeof(float2), st));
+  DCS_TRY(ctx->mag.ensure((size_t)plane * sizeof(float), st));
+  DCS_TRY(ctx->S.ensure((size_t)m->nsrc * plane * sizeof(float2), st));
+  DCS_TRY(ctx->net[7].ensure((size_t)4 * plane * sizeof(float), st));
+  float2* X = ctx->X.as<float2>();
+  float* mag = ctx->mag.as<float>();
+  float2* S = ctx->S.as<float2>();
+  float* chans = ctx->net[7].as<float>();
+  { ProfScope ps(ctx, "stft_fwd", st); DCS_TRY(launch_stft(p, d_audio, L, X, mag, nullptr, scale_factor, ldf, st)); }
+  { ProfScope ps(ctx, "score_channels", st); DCS_TRY(launch_channel_mul(ctx, mag, d_filters, chans, plane, 4, st)); }
+  DCS_TRY(sconv_forward(ctx, m, chans, plane, X, T, ldf, overlap, patcher, S, plane, st));
+  ProfScope ps(ctx, "istft_ola", st);
+  return launch_istft(p, S, nullptr, nullptr, 1.f, m->nsrc, T, ldf, plane, d_stems, L, stem_stride, st);
 }
 
 int dcs_gemm_f32(dcs_ctx* ctx, int engine, const float* d_A, int64_t lda, const float* h_B, int64_t ldb,

@@ -127,7 +127,8 @@ struct dcs_model {
 namespace dcs {
 int upload(const std::vector<float>& h, float** d);
 int model_create_sconv(dcs_model* m, int nparams, const float* const* hp, const int64_t* shp, const int* nd);
-int sconv_forward(dcs_ctx* ctx, dcs_model* m, const float* d_mag, const float2* d_X, int64_t T, int64_t ldf,
+// d_in: nch planes [T][ldf] (plane stride in_plane elements; nch = 1: the scaled magnitude)
+int sconv_forward(dcs_ctx* ctx, dcs_model* m, const float* d_in, int64_t in_plane, const float2* d_X, int64_t T, int64_t ldf,
                   int overlap, int patcher, float2* d_S, int64_t src_stride, cudaStream_t st);
 // (re)zero a workspace buffer whenever what it holds changes layout: zero padding is relied upon
 int ensure_layout(dcs_ctx* ctx, int idx, size_t bytes, uint64_t sig, cudaStream_t st);
@@ -204,6 +205,7 @@ struct SconvMaskArgs {
 };
 int launch_pool4(dcs_ctx* ctx, const float* H1, float* Hp, uint8_t* tie, int64_t rows, int J, int WP, cudaStream_t st);
 int launch_sconv_mask(dcs_ctx* ctx, const SconvMaskArgs& a, cudaStream_t st);
+int launch_channel_mul(dcs_ctx* ctx, const float* mag, const float* filt, float* out, int64_t plane, int nch, cudaStream_t st);
 bool dsd_mask_tc_supported(const DsdMaskArgs& a);
 int launch_dsd_mask_tc(dcs_ctx* ctx, const DsdMaskArgs& a, cudaStream_t st);
 

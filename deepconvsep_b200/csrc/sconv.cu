@@ -36,19 +36,19 @@ __global__ void pool4_kernel(const float* __restrict__ H1, float* __restrict__ H
 constexpr int SC_TILE = 128;   // m values (threads) per CTA
 constexpr int SC_MAXP = 6;
 
-template <int STRIDE, int ND, int NSRC, int NDEC, int RULE, int POOL>
+template <int STRIDE, int ND, int NSRC, int NDEC, int RULE, int POOL, int NW>
 __global__ void __launch_bounds__(SC_TILE)
 sconv_mask_kernel(const SconvMaskArgs a) {
   constexpr int JT = SC_TILE + ND - 1;  // staged activation positions per tile
   extern __shared__ __align__(16) float sm[];
   float* gs = sm;                                   // [NDEC][JT][33]
-  float4* ws = reinterpret_cast<float4*>(sm + NDEC * JT * 33 + (4 - (NDEC * JT * 33) % 4) % 4);  // [ND][32]
+  float4* ws = reinterpret_cast<float4*>(sm + NDEC * JT * 33 + (4 - (NDEC * JT * 33) % 4) % 4);  // [NW][ND][32]
   const int tid = threadIdx.x;
   const int m0 = blockIdx.x * SC_TILE, m = m0 + tid;
   const int t = blockIdx.y;
   const int step = a.tc - a.overlap;
   // weights: w[dd][f][r] = W1[f][KW-1 - r - STRIDE*dd] (0 where the tap index is negative)
-  for (int i = tid; i < ND * 32; i += SC_TILE) ws[i] = reinterpret_cast<const float4*>(a.W)[i];
+  for (int i = tid; i < NW * ND * 32; i += SC_TILE) ws[i] = reinterpret_cast<const float4*>(a.W)[i];
   int k_hi = t / step;
   if (k_hi > a.P - 1) k_hi = a.P - 1;
   int k_lo = t - a.tc + 1;
@@ -90,10 +90,14 @@ sconv_mask_kernel(const SconvMaskArgs a) {
       const float* grow = gs + (tid + ND - 1 - dd) * 33;
 #pragma unroll 6
       for (int f = 0; f < 30; ++f) {
-        const float4 w = ws[dd * 32 + f];
-        const float wr[4] = {w.x, w.y, w.z, w.w};
+        // NW == 1: one filter bank, one decoder per source (iKala, Bach10);
+        // NW == NSRC, NDEC == 1: one decoder, one filter bank per source = per input channel
+        // of the tied conv1 (score-informed Bach10, trainCNNrwc.py:189,248-251)
+        const float4 w0 = ws[dd * 32 + f];
 #pragma unroll
         for (int o = 0; o < NSRC; ++o) {
+          const float4 w = NW == 1 ? w0 : ws[(o * ND + dd) * 32 + f];
+          const float wr[4] = {w.x, w.y, w.z, w.w};
           const float g = grow[(NDEC == 1 ? 0 : o) * JT * 33 + f];
 #pragma unroll
           for (int r = 0; r < STRIDE; ++r) acc[o][r] = fmaf(g, wr[r], acc[o][r]);
@@ -130,6 +134,23 @@ sconv_mask_kernel(const SconvMaskArgs a) {
   }
 }
 
+// score-informed input channels: in_ch[t][b] = filter_ch[t][b] * mag[t][b]   (trainCNNrwc.py:388-391)
+__global__ void channel_mul_kernel(const float* __restrict__ mag, const float* __restrict__ filt, float* __restrict__ out,
+                                   int64_t plane, int nch) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= plane) return;
+  const float m = mag[i];
+  for (int c = 0; c < nch; ++c) out[c * plane + i] = filt[c * plane + i] * m;
+}
+
+int launch_channel_mul(dcs_ctx* ctx, const float* mag, const float* filt, float* out, int64_t plane, int nch, cudaStream_t st) {
+  if (plane <= 0) return DCS_OK;
+  channel_mul_kernel<<<(unsigned)ceil_div64(plane, 256), 256, 0, st>>>(mag, filt, out, plane, nch);
+  DCS_CHECK_LAUNCH();
+  ctx->launches++;
+  return DCS_OK;
+}
+
 int launch_pool4(dcs_ctx* ctx, const float* H1, float* Hp, uint8_t* tie, int64_t rows, int J, int WP, cudaStream_t st) {
   const int64_t total = rows * WP * 32;
   if (total <= 0) return DCS_OK;
@@ -139,19 +160,19 @@ int launch_pool4(dcs_ctx* ctx, const float* H1, float* Hp, uint8_t* tie, int64_t
   return DCS_OK;
 }
 
-template <int STRIDE, int ND, int NSRC, int NDEC, int RULE, int POOL>
+template <int STRIDE, int ND, int NSRC, int NDEC, int RULE, int POOL, int NW>
 static int launch_sconv_t(dcs_ctx* ctx, const SconvMaskArgs& a, cudaStream_t st) {
   constexpr int JT = SC_TILE + ND - 1;
-  const size_t smem = (size_t)(NDEC * JT * 33 + 4) * sizeof(float) + ND * 32 * sizeof(float4);
+  const size_t smem = (size_t)(NDEC * JT * 33 + 4) * sizeof(float) + NW * ND * 32 * sizeof(float4);
   static bool attr = false;
   if (!attr) {
-    DCS_CUDA(cudaFuncSetAttribute(sconv_mask_kernel<STRIDE, ND, NSRC, NDEC, RULE, POOL>,
+    DCS_CUDA(cudaFuncSetAttribute(sconv_mask_kernel<STRIDE, ND, NSRC, NDEC, RULE, POOL, NW>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
   const int mtot = (a.F + STRIDE - 1) / STRIDE;
   dim3 grid((unsigned)ceil_div64(mtot, SC_TILE), (unsigned)a.T);
-  sconv_mask_kernel<STRIDE, ND, NSRC, NDEC, RULE, POOL><<<grid, SC_TILE, smem, st>>>(a);
+  sconv_mask_kernel<STRIDE, ND, NSRC, NDEC, RULE, POOL, NW><<<grid, SC_TILE, smem, st>>>(a);
   DCS_CHECK_LAUNCH();
   ctx->launches++;
   return DCS_OK;
@@ -162,9 +183,10 @@ int launch_sconv_mask(dcs_ctx* ctx, const SconvMaskArgs& a, cudaStream_t st) {
   DCS_REQUIRE(a.T <= 65535, "sconv_mask: clip too long (%d frames)", a.T);
   const int step = a.tc - a.overlap;
   DCS_REQUIRE(step > 0 && (a.tc + step - 1) / step <= 64, "sconv_mask: bad time_context/overlap");
-  if (a.arch == DCS_ARCH_BACH10) return launch_sconv_t<4, 8, 4, 4, 1, 0>(ctx, a, st);
-  if (a.arch == DCS_ARCH_IKALA) return launch_sconv_t<3, 10, 2, 2, 0, 4>(ctx, a, st);
-  if (a.arch == DCS_ARCH_IKALA_NOPOOL) return launch_sconv_t<3, 10, 2, 2, 0, 0>(ctx, a, st);
+  if (a.arch == DCS_ARCH_BACH10) return launch_sconv_t<4, 8, 4, 4, 1, 0, 1>(ctx, a, st);
+  if (a.arch == DCS_ARCH_BACH10_SCORE) return launch_sconv_t<4, 8, 4, 1, 1, 0, 4>(ctx, a, st);
+  if (a.arch == DCS_ARCH_IKALA) return launch_sconv_t<3, 10, 2, 2, 0, 4, 1>(ctx, a, st);
+  if (a.arch == DCS_ARCH_IKALA_NOPOOL) return launch_sconv_t<3, 10, 2, 2, 0, 0, 1>(ctx, a, st);
   DCS_REQUIRE(false, "sconv_mask: architecture %d not supported", a.arch);
 }
 

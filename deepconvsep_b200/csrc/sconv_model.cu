@@ -35,8 +35,14 @@ int model_create_sconv(dcs_model* m, int nparams, const float* const* hp, const 
   const int F = m->F, tc = m->tc, C = 30, CP = 32, KW = 30;
   c.nch = 1;
   c.nfc = 256;
+  int ndec_params = 0;   // decoders present in the parameter list (>= the ones inference needs)
   if (m->arch == DCS_ARCH_BACH10) {
     c.sw1 = 4; c.pool = 0; c.kh2 = (2 * tc) / 3; c.kw2 = 1; c.ndec = 4; c.rule = 1; m->nsrc = 4;
+  } else if (m->arch == DCS_ARCH_BACH10_SCORE) {
+    // 4 input channels; every InverseLayer(., conv1) returns 4 channels, the concat has 16 and only
+    // channels 0..3 -- all from decoder 1 -- are used: decoders 2-4 are dead at inference
+    // (trainCNNrwc.py:189,248-251)
+    c.nch = 4; c.sw1 = 4; c.pool = 0; c.kh2 = (2 * tc) / 3; c.kw2 = 1; c.ndec = 1; ndec_params = 4; c.rule = 1; m->nsrc = 4;
   } else {
     c.sw1 = 3; c.pool = m->arch == DCS_ARCH_IKALA ? 4 : 0; c.kh2 = 10; c.kw2 = 20; c.ndec = 2; c.rule = 0; m->nsrc = 2;
   }
@@ -50,21 +56,24 @@ int model_create_sconv(dcs_model* m, int nparams, const float* const* hp, const 
   c.WPP = c.w2 + 2 * (c.kw2 - 1);
   const int h2 = c.h2, w2 = c.w2, kh2 = c.kh2, kw2 = c.kw2, ndec = c.ndec;
   const int64_t flat = (int64_t)C * h2 * w2, flatp = (int64_t)h2 * w2 * CP;
-  const int want = 8 + 2 * ndec + 1;
+  if (!ndec_params) ndec_params = ndec;
+  const int want = 8 + 2 * ndec_params + 1, nout = ndec_params * c.nch == 16 ? 16 : m->nsrc;
   if (nparams != want) { set_error("architecture %d needs %d parameter arrays, got %d", m->arch, want, nparams); return DCS_EMODEL; }
-  bool ok = shp_is(shp + 0, nd[0], 4, C, 1, 1, KW) && shp_is(shp + 4, nd[1], 1, C) && shp_is(shp + 8, nd[2], 1, C) &&
+  bool ok = shp_is(shp + 0, nd[0], 4, C, c.nch, 1, KW) && shp_is(shp + 4, nd[1], 1, C) && shp_is(shp + 8, nd[2], 1, C) &&
             shp_is(shp + 12, nd[3], 4, C, C, kh2, kw2) && shp_is(shp + 16, nd[4], 1, C) && shp_is(shp + 20, nd[5], 1, C) &&
             shp_is(shp + 24, nd[6], 2, flat, c.nfc) && shp_is(shp + 28, nd[7], 1, c.nfc) &&
-            shp_is(shp + 4 * (want - 1), nd[want - 1], 1, m->nsrc);
-  for (int d = 0; d < ndec && ok; ++d)
+            shp_is(shp + 4 * (want - 1), nd[want - 1], 1, nout);
+  for (int d = 0; d < ndec_params && ok; ++d)
     ok = shp_is(shp + 4 * (8 + 2 * d), nd[8 + 2 * d], 2, c.nfc, flat) && shp_is(shp + 4 * (9 + 2 * d), nd[9 + 2 * d], 1, flat);
   if (!ok) { set_error("parameter shapes do not match architecture %d with feat_size=%d time_context=%d", m->arch, F, tc); return DCS_EMODEL; }
 
   const float *W1 = hp[0], *W2 = hp[3], *Wfc = hp[6];
-  // conv1 forward: B1[q'][f] = W1[f][0][0][KW-1-q']
-  std::vector<float> B1((size_t)KW * C), b1(CP, 0.f), b2(CP, 0.f);
+  // conv1 forward: B1[ch*KW + q'][f] = W1[f][ch][0][KW-1-q']
+  const int nch = c.nch;
+  std::vector<float> B1((size_t)nch * KW * C), b1(CP, 0.f), b2(CP, 0.f);
   for (int f = 0; f < C; ++f)
-    for (int q = 0; q < KW; ++q) B1[(size_t)q * C + f] = W1[(size_t)f * KW + (KW - 1 - q)];
+    for (int ch = 0; ch < nch; ++ch)
+      for (int q = 0; q < KW; ++q) B1[((size_t)ch * KW + q) * C + f] = W1[((size_t)f * nch + ch) * KW + (KW - 1 - q)];
   for (int f = 0; f < C; ++f) { b1[f] = hp[1][f] + hp[2][f]; b2[f] = hp[4][f] + hp[5][f]; }
   // conv2 forward / transposed: K index ((p'*kw2 + q')*32 + channel)
   const size_t K2 = (size_t)kh2 * kw2 * CP;
@@ -77,7 +86,7 @@ int model_create_sconv(dcs_model* m, int nparams, const float* const* hp, const 
           B2[(((size_t)(kh2 - 1 - p) * kw2 + (kw2 - 1 - q)) * CP + ci) * C + fo] = v;  // out channel fo <- in ci
           Bt2[(((size_t)p * kw2 + q) * CP + fo) * C + ci] = v;                        // InverseLayer: in fo -> out ci
         }
-  DCS_TRY(tc_weight_create(B1.data(), C, KW, C, &c.tW[0]));
+  DCS_TRY(tc_weight_create(B1.data(), C, nch * KW, C, &c.tW[0]));
   DCS_TRY(tc_weight_create(B2.data(), C, (int)K2, C, &c.tW[1]));
   DCS_TRY(tc_weight_create(Bt2.data(), C, (int)K2, C, &c.tW[3]));
   {  // bottleneck: rows permuted from Lasagne's (f', i, v) flattening to (i, v, f' padded to 32)
@@ -104,15 +113,16 @@ int model_create_sconv(dcs_model* m, int nparams, const float* const* hp, const 
     DCS_TRY(upload(bb, &c.bdec[d]));
     m->dev.push_back(c.bdec[d]);
   }
-  // K3s filter bank: w[dd][f][r] = W1[f][KW-1-r-sw1*dd]
+  // K3s filter banks (one per conv1 input channel): w[ch][dd][f][r] = W1[f][ch][KW-1-r-sw1*dd]
   const int ND = (KW + c.sw1 - 1) / c.sw1;
-  std::vector<float> Wsc((size_t)ND * 32 * 4, 0.f);
-  for (int dd = 0; dd < ND; ++dd)
-    for (int f = 0; f < C; ++f)
-      for (int r = 0; r < c.sw1; ++r) {
-        const int q = KW - 1 - r - c.sw1 * dd;
-        if (q >= 0) Wsc[((size_t)dd * 32 + f) * 4 + r] = W1[(size_t)f * KW + q];
-      }
+  std::vector<float> Wsc((size_t)nch * ND * 32 * 4, 0.f);
+  for (int ch = 0; ch < nch; ++ch)
+    for (int dd = 0; dd < ND; ++dd)
+      for (int f = 0; f < C; ++f)
+        for (int r = 0; r < c.sw1; ++r) {
+          const int q = KW - 1 - r - c.sw1 * dd;
+          if (q >= 0) Wsc[(((size_t)ch * ND + dd) * 32 + f) * 4 + r] = W1[((size_t)f * nch + ch) * KW + q];
+        }
   std::vector<float> bfc(hp[7], hp[7] + c.nfc), bout(hp[want - 1], hp[want - 1] + m->nsrc);
   struct { const std::vector<float>* h; float** d; } ups[] = {{&b1, &c.b1}, {&b2, &c.b2}, {&bfc, &c.bfc}, {&bout, &c.bout}, {&Wsc, &c.Wsc}};
   for (auto& u : ups) {
@@ -122,7 +132,7 @@ int model_create_sconv(dcs_model* m, int nparams, const float* const* hp, const 
   return DCS_OK;
 }
 
-int sconv_forward(dcs_ctx* ctx, dcs_model* m, const float* d_mag, const float2* d_X, int64_t T, int64_t ldf,
+int sconv_forward(dcs_ctx* ctx, dcs_model* m, const float* d_in, int64_t in_plane, const float2* d_X, int64_t T, int64_t ldf,
                   int overlap, int patcher, float2* d_S, int64_t src_stride, cudaStream_t st) {
   const dcs_sconv& c = m->sc;
   const int tc = m->tc, step = tc - overlap, CP = 32, C = 30;
@@ -155,8 +165,9 @@ int sconv_forward(dcs_ctx* ctx, dcs_model* m, const float* d_mag, const float2* 
 
   {  // conv1 + biases: rows (t, j) are 30-sample windows of the magnitude frame, stride sw1
     ProfScope ps(ctx, "enc_conv1_gemm", st);
-    GemmDesc g = gemm_plain(d_mag, 0, nullptr, C, c.b1, H1, CP, (int)(Tp * J), C, 30, 0);
+    GemmDesc g = gemm_plain(d_in, 0, nullptr, C, c.b1, H1, CP, (int)(Tp * J), C, 30 * c.nch, 0);
     g.m_inner = J; g.a_so = ldf; g.a_si = c.sw1;
+    g.k_seg = 30; g.k_ss = in_plane;      // one 30-tap segment per input channel
     g.a_valid_rows = (int)(T * J);
     DCS_TRY(launch_gemm_tc(ctx, g, c.tW[0], st));
   }

@@ -268,6 +268,28 @@ class Separator(object):
                                                _stream_ptr(stream)))
         return out
 
+    def separate_score(self, audio, filters, out=None, stream=None):
+        """Score-informed Bach10: audio float [L] (numpy or cuda tensor) + normalised score filters
+        [4, T, F] float32 (deepconvsep_b200.score.score_filters) -> stems float32 [4, L] (same kind as
+        `audio`).  The filters are uploaded, the four input channels are formed on the device."""
+        import torch
+        host = not hasattr(audio, "is_cuda")
+        x = torch.as_tensor(np.ascontiguousarray(audio, dtype=np.float32), device="cuda") if host else audio
+        L = x.numel()
+        T = self.stft.num_frames(L)
+        f = np.asarray(filters, dtype=np.float32)
+        assert f.shape == (4, T, self.model.F), (f.shape, (4, T, self.model.F))
+        fd = torch.zeros((4, T, self.stft.ldf), dtype=torch.float32, device=x.device)
+        fd[:, :, :self.model.F] = torch.as_tensor(f, device=x.device)
+        if out is None or host:
+            outd = torch.empty((self.nsrc, L), dtype=torch.float32, device=x.device)
+        else:
+            outd = out
+        _lib.check(self.lib.dcs_separate_audio_score(self.ctx.handle, self.model.handle, self.stft.handle, _ptr(x), L,
+                                                     _ptr(fd), self.scale_factor, self.overlap, self.patcher, _ptr(outd),
+                                                     outd.stride(0), _stream_ptr(stream)))
+        return outd.cpu().numpy() if host else outd
+
     def separate_spec(self, mag, X, stream=None):
         """scaled magnitude [T, ldf] + mixture STFT [T, ldf] -> masked spectra complex64 [nsrc, T, ldf]"""
         import torch

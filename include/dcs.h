@@ -128,6 +128,19 @@ int dcs_separate_spec(dcs_ctx* ctx, dcs_model* model, const float* d_mag, const 
                       int64_t num_frames, int64_t ldf, int overlap, int patcher, dcs_complex* d_S,
                       int64_t src_stride, void* stream);
 
+/* Score-informed Bach10 (examples/bach10_scoreinformed/trainCNNrwc.py:357-416): the network sees 4
+ * input channels in_ch = filter_ch * scaled magnitude, where filter_ch[T][F] are the normalised
+ * harmonic masks derived from the scores on the host (LargeDatasetMask2.filterSpec,
+ * dataset.py:839-879; deepconvsep_b200/score.py).  d_in: 4 planes [T][ldf], plane stride in_plane. */
+int dcs_separate_spec_channels(dcs_ctx* ctx, dcs_model* model, const float* d_in, int64_t in_plane,
+                               const dcs_complex* d_X, int64_t num_frames, int64_t ldf, int overlap,
+                               int patcher, dcs_complex* d_S, int64_t src_stride, void* stream);
+/* whole path on device buffers: d_filters float[4][T][ldf] (ldf = dcs_padded_bins(N), pad columns
+ * arbitrary), d_audio float[L] -> d_stems float[4][stem_stride] */
+int dcs_separate_audio_score(dcs_ctx* ctx, dcs_model* model, dcs_stft* plan, const float* d_audio,
+                             int64_t num_samples, const float* d_filters, float scale_factor, int overlap,
+                             int patcher, float* d_stems, int64_t stem_stride, void* stream);
+
 /* ---- building block: the dense layer / im2col-free convolution GEMM ------------------------ */
 /* d_C[M][ldc] = act(d_A[M][lda] * h_B[K][ldb] (+ h_bias[N])), fp32 in / fp32 out.  The weight is a
  * HOST array (it is transposed, padded and split for the tensor cores on the fly -- the models

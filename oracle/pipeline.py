@@ -77,6 +77,44 @@ def separate(audio, params, arch, frameSize=1024, hopSize=512, window=np.hanning
     return stems
 
 
+def separate_score(audio, filters, params, frameSize=4096, hopSize=512, window=None, scale_factor=0.2,
+                   time_context=30, overlap=25, batch_size=32, count_kinks=False):
+    """Score-informed separation branch of examples/bach10_scoreinformed/trainCNNrwc.py:384-416:
+    filters [4, T, F] float32 (LargeDatasetMask2.filterSpec) -> input channels filter*mag (float32
+    products), util's zero-padded patcher on the 3-D tensor, network + Bach10 mask rule on the sum
+    of the channels, cross-fade, inverse STFT with the mixture phase."""
+    if window is None:
+        window = dsp.blackmanharris
+    arch = "bach10_score"
+    a = nets.ARCHS[arch]
+    mag, ph = dsp.compute_file(audio, phase=True, frameSize=frameSize, hopSize=hopSize, window=window)
+    mag = scale_factor * mag.astype(np.float32)
+    masks = np.ones((4, mag.shape[0], mag.shape[1]))
+    for j in range(4):
+        masks[j] = np.asarray(filters[j], dtype=np.float32) * mag
+    batches, nchunks = patch.generate_overlapadd_util(masks, input_size=masks.shape[-1], time_context=time_context,
+                                                      overlap=overlap, batch_size=batch_size)
+    output = np.array([nets.predict_function2(params, b, arch) for b in batches])
+    kink_energy = 0.0
+    if count_kinks:
+        nk, left = 0, nchunks
+        for b in batches:
+            nb = max(0, min(left, batch_size))
+            flag = nets.near_kink(nets.predict(params, b, arch, return_pre=True)[:nb], a["mask"], a["nsrc"])
+            nk += int(flag.sum())
+            kink_energy += float((flag * b[:nb].sum(axis=1) ** 2).sum())
+            left -= batch_size
+        separate_score.last_kinks = nk
+    mm = patch.overlapadd_multi(output, batches, nchunks, overlap=overlap)
+    if count_kinks:
+        separate_score.last_kink_bound = [float(np.sqrt(kink_energy / max(float((mm[i] ** 2).sum()), 1e-300))) for i in range(4)]
+    stems = []
+    for i in range(4):
+        audio_out = dsp.compute_inverse(mm[i, :len(ph)] / scale_factor, ph, frameSize=frameSize, hopSize=hopSize, window=window)
+        stems.append(audio_out[:len(audio)] if len(audio_out) > len(audio) else audio_out)
+    return np.stack(stems)
+
+
 def synth_mixture(seconds, seed, sr=44100):
     """Seeded synthetic 4-stem mixture: harmonic tone with vibrato,
     low sine bursts, noise bursts, pink-ish noise; int16-quantised like a wav file.

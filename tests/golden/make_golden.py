@@ -88,5 +88,80 @@ def main():
     print("wrote", os.path.join(HERE, "dsp_golden.npz"), len(out), "arrays")
 
 
+# ---------------------------------------------------------------------------------------------
+# score prelude of the score-informed path: util.getMidiNum / expandMidi / slicefft_slices / str2midi
+# and LargeDatasetMask2.filterSpec, executed from the reference source (Python-2 idioms shimmed:
+# `filter` returns a list, note names read as bytes are decoded before str2midi).
+def grab_method(path, cls_marker, name):
+    src = open(os.path.join(REF, path)).read()
+    i = src.index(cls_marker)
+    m = re.search(r"^    def %s\(.*?(?=^    def |\Z)" % re.escape(name), src[i:], re.S | re.M)
+    assert m, (path, name)
+    import textwrap
+    return textwrap.dedent(m.group(0))
+
+
+SCORES = {
+    "bassoon_b": "0.10,0.80,C3\n0.90,1.60,E3\n1.70,2.90,G2\n3.00,3.02,A2\n3.10,3.90,C#3\n",
+    "clarinet_b": "0.00,0.70,E4\n0.75,1.50,G4\n1.50,2.20,Bb4\n2.60,3.80,A4\n",
+    "saxophone_b": "0.20,1.00,G3\n1.00,2.00,B3\n2.10,2.80,D4\n2.80,3.95,F#3\n",
+    "violin_b": "0.05,0.60,C5\n0.60,1.20,D5\n1.25,2.40,E5\n2.40,3.00,F5\n3.20,3.90,G5\n",
+}
+
+
+def score_golden():
+    import itertools
+    import tempfile
+    import builtins
+    from bisect import bisect_left, bisect_right
+    src = open(os.path.join(REF, "util.py")).read()
+    ns = {"np": np, "os": os, "it": itertools, "bisect_left": bisect_left, "bisect_right": bisect_right,
+          "nan": float("nan"), "filter": lambda f, l: list(builtins.filter(f, l)), "MIDI_A4": 69}
+    for name in ["midi2freq", "getfreqs", "remove_overlap", "slicefft_slices", "str2midi", "getMidiNum", "expandMidi"]:
+        m = re.search(r"^def %s\(.*?(?=^(?:def |class |#+ )|\Z)" % re.escape(name), src, re.S | re.M)
+        assert m, name
+        exec(compile(m.group(0), "util.py:" + name, "exec"), ns)
+    orig = ns["str2midi"]
+    ns["str2midi"] = lambda n: orig(n.decode("ascii") if isinstance(n, bytes) else n)
+    fs_src = grab_method("dataset.py", "class LargeDatasetMask2", "filterSpec")
+    fns = {"np": np}
+    exec(compile(fs_src, "dataset.py:filterSpec", "exec"), fns)
+
+    class Dummy(object):
+        tensortype = np.float32
+        timbre_model_path = None
+    out = {}
+    d = tempfile.mkdtemp()
+    for k, v in SCORES.items():
+        open(os.path.join(d, k + ".txt"), "w").write(v)
+        out["txt_" + k] = np.frombuffer(v.encode("ascii"), dtype=np.uint8)
+    insts = ["bassoon_b", "clarinet_b", "saxophone_b", "violin_b"]
+    nharm, frameSize, hop, sr = 20, 4096, 512, 44100
+    nframes = int(np.ceil(4.0 * sr / float(hop))) + 2
+    nelem = 1
+    for i, inst in enumerate(insts):
+        ng = ns["getMidiNum"](inst, d, 0, 40.0)
+        out["num_%d" % i] = np.array(ng)
+        nelem = max(nelem, ng)
+    melody = np.zeros((4, nelem, 2 * nharm + 3))
+    for i, inst in enumerate(insts):
+        tmp = ns["expandMidi"](inst, d, 0, 40.0, 50, 440, nharm, sr, hop, frameSize, 0.2, 0.2, nframes, 0.5)
+        out["exp_%d" % i] = tmp
+        melody[i, :tmp.shape[0], :] = tmp
+    rng = np.random.default_rng(5)
+    mag = (0.3 * np.abs(rng.standard_normal((nframes, frameSize // 2 + 1)))).astype(np.float32)
+    mask = fns["filterSpec"](Dummy(), mag, melody, 0, nframes)
+    out["melody"] = melody
+    out["mask"] = mask
+    out["nframes"] = np.array(nframes)
+    out["str2midi"] = np.array([ns["str2midi"](s) for s in ["C3", "Bb4", "F#3", "C#5", "A4", "Ebb2", "Gx6"]], dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "score_golden.npz"), **out)
+    print("wrote score_golden.npz", len(out), "arrays; mask", mask.shape, "ones", int((mask > 0.99).sum()))
+
+
 if __name__ == "__main__":
-    sys.exit(main())
+    if "--score" in sys.argv:
+        score_golden()
+    else:
+        main()
+        score_golden()

@@ -82,3 +82,36 @@ def test_models_share_a_context_safely():
                 assert max(rel(out[s].astype(np.float64), want[s]) for s in range(4)) < 5e-4
             else:
                 assert np.array_equal(out, outs[arch])
+
+
+def test_score_informed_bach10():
+    """4-channel score-conditioned network (trainCNNrwc.py:134-263): only decoder 1 is live, the four
+    sources are the four input-channel filter banks of the tied conv1; util patcher, scale 0.2."""
+    from deepconvsep_b200.engine import Separator
+    F, N, hop = 129, 256, 128
+    params = nets.make_synthetic_params("bach10_score", F, seed=8)
+    assert len(params) == 17 and params[0].shape == (30, 4, 1, 30) and params[-1].shape == (16,)
+    mix, _ = pipeline.synth_mixture(1.0, 91)
+    T = dsp.num_frames(mix.size, hop)
+    rng = np.random.default_rng(4)
+    # synthetic "score" filters with the structure filterSpec produces: 1 on note bins, 1e-18 elsewhere, normalised
+    raw = np.full((4, T, F), 1e-18, dtype=np.float32)
+    for j in range(4):
+        for _ in range(6):
+            t0, b0 = rng.integers(0, T - 40), rng.integers(1, F - 12)
+            raw[j, t0:t0 + 40, b0:b0 + 8] = 1.0
+    filters = (raw / raw.sum(axis=0)).astype(np.float32)
+    want = pipeline.separate_score(mix, filters, params, frameSize=N, hopSize=hop, window=dsp.blackmanharris,
+                                   scale_factor=0.2, overlap=25, count_kinks=True)
+    kinks, bound = pipeline.separate_score.last_kinks, pipeline.separate_score.last_kink_bound
+    sep = Separator(params, arch="bach10_score", frame_size=N, hop=hop, window="blackmanharris", overlap=25,
+                    patcher="util", scale_factor=0.2, feat_size=F)
+    got = sep.separate_score(mix, filters)
+    assert got.shape == want.shape == (4, mix.size)
+    assert min(np.linalg.norm(w) for w in want) > 0.02 * np.linalg.norm(mix)
+    for s in range(4):
+        e = rel(got[s].astype(np.float64), want[s])
+        allow = TOL if not kinks else TOL + 1.5 * bound[s]
+        assert e <= allow, (s, e, allow, kinks)
+    with pytest.raises(Exception):
+        sep.separate(mix)          # the single-channel entry point must refuse this architecture

@@ -72,7 +72,9 @@ def test_cli_usage_and_descriptors(capsys):
     import deepconvsep_b200.examples.hiphopss.separate_hhds as sh
     import deepconvsep_b200.examples.ikala.separate_ikala as si
     import deepconvsep_b200.examples.bach10.separate_bach10 as sb
-    for mod in (sd, sh, si, sb):
+    import deepconvsep_b200.examples.bach10_scoreinformed.separate_bach10 as ss
+    assert ss.build_ca()["nchannels"] == 4
+    for mod in (sd, sh, si, sb, ss):
         with pytest.raises(SystemExit):
             mod.main(["-h"])
         assert "-i <inputfile> -o <outputdir> -m <path_to_model.pkl>" in capsys.readouterr().out
