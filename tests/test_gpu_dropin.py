@@ -89,3 +89,31 @@ def test_separate_dsd_cli_end_to_end(tmp_path):
     # wrong sample rate: prints and writes nothing (separate_dsd.py:313)
     scipy.io.wavfile.write(wav, 22050, pcm)
     assert separate_dsd.train_auto(wav, outdir, pkl, 0.3, 30, 25, 32, 513) is None
+
+
+def test_dataset_runner_dsd100(tmp_path):
+    """trainers' separation branch (dsd100/trainCNN.py:285-335): Dev/Test song folders, util patcher,
+    blackmanharris analysis, stems written with the input bit depth."""
+    from deepconvsep_b200 import runner
+    params = nets.make_synthetic_params("dsd", 513, seed=31)
+    db, out = tmp_path / "Mixtures", tmp_path / "Estimates"
+    songs = {("Dev", "051 - A"): 1.7, ("Test", "001 - B"): 1.2}
+    for (sub, name), secs in songs.items():
+        mix, _ = pipeline.synth_mixture(secs, hash(name) % 1000)
+        pcm = np.stack([np.round(mix * 30000), np.round(mix * 25000)], axis=1).astype(np.int16)
+        os.makedirs(str(db / sub / name))
+        scipy.io.wavfile.write(str(db / sub / name / "mixture.wav"), 44100, pcm)
+    secs, njobs = runner.separate_dataset("dsd", str(db), str(out), params)
+    assert njobs == 2 and abs(secs - 2.9) < 1e-3
+    for (sub, name), _ in songs.items():
+        sr, pcm = scipy.io.wavfile.read(str(db / sub / name / "mixture.wav"))
+        audio = (pcm[:, 0].astype(float) / 32767 + pcm[:, 1].astype(float) / 32767) / 2
+        want = pipeline.separate(audio, params, "dsd", frameSize=1024, window=dsp.blackmanharris, overlap=25,
+                                 patcher="util", count_kinks=True)
+        for i, s in enumerate(["vocals", "bass", "drums", "other"]):
+            sr2, got = scipy.io.wavfile.read(str(out / sub / name / (s + ".wav")))
+            assert sr2 == 44100 and got.dtype == np.int16
+            d = np.abs(got.astype(np.int32) - (want[i] * 32767).astype("int16").astype(np.int32))
+            assert np.mean(d > 1) < 2e-3
+    # sharding: two ranks split the two songs
+    assert len(runner.list_jobs("dsd", str(db), str(out))) == 2
