@@ -39,9 +39,10 @@ struct TcSmem {
 // round-robin over three accumulators and sends both correction terms (2^-11 smaller, their
 // truncation is harmless) to a fourth; the epilogue adds the four in fp32 registers.
 //   acc_mode 0: one accumulator for everything; 1: main + corrections; 2: 3 x main + corrections
-template <int BN, int STAGES, int AVEC>
+template <int BN, int STAGES, int AVEC, bool SPLITK>
 __global__ void __launch_bounds__(TC_THREADS)
-gemm_tc_kernel(const GemmDesc d, const float* __restrict__ Bhi, const float* __restrict__ Blo, int Kp, int acc_mode, int dbg) {
+gemm_tc_kernel(const GemmDesc d, const float* __restrict__ Bhi, const float* __restrict__ Blo, int Kp, int acc_mode, int dbg,
+               int k_splits, float* __restrict__ partial, int ldp) {
   using SM = TcSmem<BN, STAGES>;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
@@ -59,6 +60,12 @@ gemm_tc_kernel(const GemmDesc d, const float* __restrict__ Bhi, const float* __r
     kb_lo = (d.kc_unit * q_lo) / KSTAGE;
     kb_hi = min(kb_hi, (d.kc_unit * (q_hi + 1) + KSTAGE - 1) / KSTAGE);
     if (kb_hi <= kb_lo) kb_hi = kb_lo + 1;   // keep one (all-zero) block so the accumulators are defined
+  }
+  if (SPLITK) {   // split-K: this CTA (blockIdx.z) owns a contiguous slice of the k-blocks
+    const int per = (kb_hi - kb_lo + k_splits - 1) / k_splits;
+    kb_lo += blockIdx.z * per;
+    kb_hi = min(kb_hi, kb_lo + per);
+    if (kb_hi <= kb_lo) kb_hi = kb_lo + 1;   // (past the end: zero blocks, contributes an all-zero partial)
   }
   const int num_kb = kb_hi - kb_lo;   // k-block i of this tile is global block kb_lo + i
 
@@ -204,7 +211,13 @@ gemm_tc_kernel(const GemmDesc d, const float* __restrict__ Bhi, const float* __r
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] += u[i];
       }
-      if (m_ok) {
+      if (SPLITK && m_ok) {   // split-K: raw partial sums, reduced (+bias, activation) by splitk_reduce_kernel
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int n = n0 + 16 * j + i;
+          if (n < d.N) partial[((int64_t)blockIdx.z * d.M + m) * ldp + n] = v[i];
+        }
+      } else if (!SPLITK && m_ok) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int n = n0 + 16 * j + i;
@@ -253,6 +266,19 @@ gemm_tc_kernel(const GemmDesc d, const float* __restrict__ Bhi, const float* __r
   }
 }
 
+__global__ void splitk_reduce_kernel(const GemmDesc d, const float* __restrict__ partial, int ldp, int k_splits) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)d.M * d.N) return;
+  const int m = (int)(i / d.N), n = (int)(i - (int64_t)m * d.N);
+  float x = 0.f;
+  for (int z = 0; z < k_splits; ++z) x += partial[((int64_t)z * d.M + m) * ldp + n];   // fixed order: deterministic
+  if (d.bias) x += __ldg(d.bias + n);
+  if (d.relu) x = fmaxf(x, 0.f);
+  const int64_t roff = (int64_t)(m / d.cm_inner) * d.c_so + (int64_t)((m % d.cm_inner) / d.cm_inner2) * d.c_si +
+                       (int64_t)(m % d.cm_inner2) * d.c_s2 + d.c_col0;
+  d.C[roff + (int64_t)(n / d.n_seg) * d.n_ss + (n % d.n_seg)] = x;
+}
+
 // ---- host side ------------------------------------------------------------------------------
 int tc_weight_create(const float* B, int64_t ldb, int K, int N, TcWeight* out) {
   // B[k][n] row-major (ld = ldb) -> K-major Bt[n][k], zero padded to Np x Kp, split hi/lo
@@ -288,11 +314,37 @@ static int launch_tc(dcs_ctx* ctx, const GemmDesc& d, const TcWeight& w, cudaStr
   using SM = TcSmem<BN, STAGES>;
   static bool attr = false;
   if (!attr) {
-    DCS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, AVEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    DCS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, AVEC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    DCS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, AVEC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
     attr = true;
   }
-  dim3 grid((unsigned)ceil_div64(d.M, TC_BM), (unsigned)ceil_div64(d.N, BN));
-  gemm_tc_kernel<BN, STAGES, AVEC><<<grid, TC_THREADS, SM::TOTAL, st>>>(d, w.hi, w.lo, w.Kp, ctx->tc_acc_mode, ctx->tc_debug);
+  const int m_tiles = (int)ceil_div64(d.M, TC_BM), n_tiles = (int)ceil_div64(d.N, BN);
+  const int num_kb = (d.K + KSTAGE - 1) / KSTAGE;
+  // skinny GEMMs (few output tiles, long K -- the bottleneck dense layers): split K over otherwise idle SMs
+  int splits = 1;
+  if ((int64_t)m_tiles * n_tiles * 2 <= ctx->num_sms && num_kb >= 16 && d.kc_rows == 0) {
+    splits = (int)std::min<int64_t>(ctx->num_sms / ((int64_t)m_tiles * n_tiles), num_kb / 8);
+    if (splits < 2) splits = 1;
+  }
+  float* partial = nullptr;
+  const int ldp = (d.N + 3) / 4 * 4;
+  if (splits > 1) {
+    DCS_TRY(ctx->net[8].ensure((size_t)splits * d.M * ldp * sizeof(float), st));
+    partial = ctx->net[8].as<float>();
+  }
+  dim3 grid((unsigned)m_tiles, (unsigned)n_tiles, (unsigned)splits);
+  if (splits > 1)
+    gemm_tc_kernel<BN, STAGES, AVEC, true><<<grid, TC_THREADS, SM::TOTAL, st>>>(d, w.hi, w.lo, w.Kp, ctx->tc_acc_mode,
+                                                                                 ctx->tc_debug, splits, partial, ldp);
+  else
+    gemm_tc_kernel<BN, STAGES, AVEC, false><<<grid, TC_THREADS, SM::TOTAL, st>>>(d, w.hi, w.lo, w.Kp, ctx->tc_acc_mode,
+                                                                                  ctx->tc_debug, 1, nullptr, 0);
+  if (splits > 1) {
+    DCS_CHECK_LAUNCH();
+    ctx->launches++;
+    const int64_t tot = (int64_t)d.M * d.N;
+    splitk_reduce_kernel<<<(unsigned)ceil_div64(tot, 256), 256, 0, st>>>(d, partial, ldp, splits);
+  }
   DCS_CHECK_LAUNCH();
   ctx->launches++;
   return DCS_OK;
@@ -315,6 +367,11 @@ int launch_gemm_tc(dcs_ctx* ctx, const GemmDesc& d, const TcWeight& w, cudaStrea
     if (avec == 4) return launch_tc<128, 3, 4>(ctx, d, w, st);
     if (avec == 2) return launch_tc<128, 3, 2>(ctx, d, w, st);
     return launch_tc<128, 3, 1>(ctx, d, w, st);
+  }
+  if (d.N <= 32) {   // the 30-channel convolutions of the iKala / Bach10 nets: half the weight traffic and MMA time
+    if (avec == 4) return launch_tc<32, 4, 4>(ctx, d, w, st);
+    if (avec == 2) return launch_tc<32, 4, 2>(ctx, d, w, st);
+    return launch_tc<32, 4, 1>(ctx, d, w, st);
   }
   if (avec == 4) return launch_tc<64, 4, 4>(ctx, d, w, st);
   if (avec == 2) return launch_tc<64, 4, 2>(ctx, d, w, st);
