@@ -65,7 +65,7 @@ gemm_tc_kernel(const GemmDesc d, const float* __restrict__ Bhi, const float* __r
     const int per = (kb_hi - kb_lo + k_splits - 1) / k_splits;
     kb_lo += blockIdx.z * per;
     kb_hi = min(kb_hi, kb_lo + per);
-    if (kb_hi <= kb_lo) kb_hi = kb_lo + 1;   // (past the end: zero blocks, contributes an all-zero partial)
+    if (kb_hi <= kb_lo) kb_hi = kb_lo + 1;   // cannot happen (the launcher sizes the slices); loads past K are guarded
   }
   const int num_kb = kb_hi - kb_lo;   // k-block i of this tile is global block kb_lo + i
 
@@ -143,7 +143,7 @@ gemm_tc_kernel(const GemmDesc d, const float* __restrict__ Bhi, const float* __r
         const int rr = i * 16 + (tid >> 3);          // row in the stacked (hi, lo) B planes
         const int which = rr / BN, rn = rr - which * BN;
         const float* src = (which ? Blo : Bhi) + (int64_t)(n0 + rn) * Kp + (kb_lo + kb) * KSTAGE + 4 * (tid & 7);
-        rb[i] = ld_stream(reinterpret_cast<const float4*>(src));
+        rb[i] = (kb_lo + kb) * KSTAGE < Kp ? ld_stream(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
     // bring-up probes (DCS_DEBUG_TC_SKIP): bit0 = no global loads, bit1 = no MMAs, bit2 = no shared stores
@@ -282,7 +282,7 @@ __global__ void splitk_reduce_kernel(const GemmDesc d, const float* __restrict__
 // ---- host side ------------------------------------------------------------------------------
 int tc_weight_create(const float* B, int64_t ldb, int K, int N, TcWeight* out) {
   // B[k][n] row-major (ld = ldb) -> K-major Bt[n][k], zero padded to Np x Kp, split hi/lo
-  const int Kp = (K + KSTAGE - 1) / KSTAGE * KSTAGE, Np = (N + 63) / 64 * 64;
+  const int Kp = (K + KSTAGE - 1) / KSTAGE * KSTAGE, Np = (N + 127) / 128 * 128;  // the widest tile reads 128 rows
   std::vector<float> hi((size_t)Np * Kp, 0.f), lo((size_t)Np * Kp, 0.f);
   for (int k = 0; k < K; ++k)
     for (int n = 0; n < N; ++n) {
@@ -325,6 +325,10 @@ static int launch_tc(dcs_ctx* ctx, const GemmDesc& d, const TcWeight& w, cudaStr
   if ((int64_t)m_tiles * n_tiles * 2 <= ctx->num_sms && num_kb >= 16 && d.kc_rows == 0) {
     splits = (int)std::min<int64_t>(ctx->num_sms / ((int64_t)m_tiles * n_tiles), num_kb / 8);
     if (splits < 2) splits = 1;
+    if (splits > 1) {   // no empty slice: every blockIdx.z must own at least one real k-block
+      const int per = (num_kb + splits - 1) / splits;
+      splits = (num_kb + per - 1) / per;
+    }
   }
   float* partial = nullptr;
   const int ldp = (d.N + 3) / 4 * 4;
