@@ -371,7 +371,6 @@ static int dsd_forward(dcs_ctx* ctx, dcs_model* m, const float* d_mag, const flo
   DsdMaskArgs a;
   a.G = G; a.ldg = ldg; a.W1t = m->W1t; a.ldw = (int)m->ldw; a.bout = m->bout; a.X = d_X; a.S = d_S;
   a.ldf = ldf; a.src_stride = src_stride; a.T = (int)T; a.P = (int)P; a.tc = tc; a.overlap = overlap; a.F = m->F;
-  a.only_nyquist = 0;
   ProfScope ps(ctx, "dec_convT1_mask_xfade", st);
   if (!ctx->debug_simt_gemm && dsd_mask_tc_supported(a)) return launch_dsd_mask_tc(ctx, a, st);
   return launch_dsd_mask(ctx, a, st);   // FFMA kernel: > 6 patches per frame, or bring-up cross-check

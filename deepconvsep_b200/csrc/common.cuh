@@ -188,7 +188,6 @@ struct DsdMaskArgs {
   float2* S;           // [4][T][ldf]
   int64_t ldf, src_stride;
   int T, P, tc, overlap, F;
-  int only_nyquist;    // FFMA kernel: compute bin F-1 only (the tensor-core kernel did the rest)
 };
 int launch_dsd_mask(dcs_ctx* ctx, const DsdMaskArgs& a, cudaStream_t st);
 // strided-conv1 families (iKala / Bach10): K3s arguments

@@ -1,5 +1,8 @@
-// dsd.cu -- K3 for the DSD100 / hiphopss network: InverseLayer(conv1) + ConcatLayer + output
-// bias + ReLU + soft ratio mask + patch cross-fade + mixture-phase re-apply, fused.
+// dsd.cu -- K3 for the DSD100 / hiphopss network, exact-fp32 FFMA version: InverseLayer(conv1) +
+// ConcatLayer + output bias + ReLU + soft ratio mask + patch cross-fade + mixture-phase re-apply, fused.
+// The product path for the reference settings is the tensor-core kernel in dsd_tc.cu; this one
+// serves (time_context, overlap) settings with more than 6 patches per frame and the bring-up
+// cross-check (DCS_DEBUG_SIMT_GEMM=1).
 //
 // Reference: examples/dsd100/separate_dsd.py:212-234 (l_inverse4x, l_merge, l_out), :258-271 (masks),
 // :139-169 (overlapadd_multi), :304 + :36-41 (compute_inverse).  Because conv1 spans the whole
@@ -31,7 +34,7 @@ dsd_mask_kernel(const DsdMaskArgs a, int frames_per_cta) {
   int b = -1;
   if (tid < MASK_TILE) {
     const int bb = blockIdx.x * MASK_TILE + tid;
-    if (bb < a.F - 1 && !a.only_nyquist) b = bb;
+    if (bb < a.F - 1) b = bb;
   } else if (tid == MASK_TILE && blockIdx.x == 0) {
     b = a.F - 1;
   }
@@ -121,7 +124,7 @@ int launch_dsd_mask(dcs_ctx* ctx, const DsdMaskArgs& a, cudaStream_t st) {
   if (a.T <= 0) return DCS_OK;
   DCS_REQUIRE(a.tc > a.overlap && a.overlap >= 0, "time_context %d must exceed overlap %d", a.tc, a.overlap);
   const int fpc = 16;
-  dim3 grid(a.only_nyquist ? 1u : (unsigned)ceil_div64(a.F - 1, MASK_TILE), (unsigned)ceil_div64(a.T, fpc));
+  dim3 grid((unsigned)ceil_div64(a.F - 1, MASK_TILE), (unsigned)ceil_div64(a.T, fpc));
   dsd_mask_kernel<50><<<grid, MASK_THREADS, 0, st>>>(a, fpc);
   DCS_CHECK_LAUNCH();
   ctx->launches++;

@@ -34,7 +34,6 @@ __global__ void pool4_kernel(const float* __restrict__ H1, float* __restrict__ H
 }
 
 constexpr int SC_TILE = 128;   // m values (threads) per CTA
-constexpr int SC_MAXP = 6;
 
 template <int STRIDE, int ND, int NSRC, int NDEC, int RULE, int POOL, int NW>
 __global__ void __launch_bounds__(SC_TILE)
