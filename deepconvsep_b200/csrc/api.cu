@@ -93,6 +93,16 @@ int dcs_create(int device, dcs_ctx** out) {
   c->debug_smem_fft = sf && sf[0] == '1';
   const char* am = getenv("DCS_DEBUG_TC_ACC");
   if (am && am[0] >= '0' && am[0] <= '2') c->tc_acc_mode = am[0] - '0';
+  const char* tm = getenv("DCS_DEBUG_TMA");
+  if (tm && tm[0] >= '0' && tm[0] <= '2') c->tma_mode = tm[0] - '0';
+  const char* ts = getenv("DCS_DEBUG_TMA_STAGES");
+  if (ts && (ts[0] == '2' || ts[0] == '4')) c->tma_stages = ts[0] - '0';
+  const char* tn = getenv("DCS_DEBUG_TMA_WIDE");
+  c->tma_wide = tn && tn[0] == '1';
+  const char* tk = getenv("DCS_DEBUG_TMA_MASK");
+  if (tk && tk[0] >= '0' && tk[0] <= '9') c->tma_mask = atoi(tk);
+  const char* ty = getenv("DCS_DEBUG_TMA_SYNC");
+  c->tma_sync = ty && ty[0] == '1';
   *out = c;
   return DCS_OK;
 }
@@ -247,8 +257,14 @@ static int model_create_dsd(dcs_model* m, int nparams, const float* const* hp, c
   const int64_t ldf = dcs_padded_bins(2 * (F - 1));
   m->ldw = ldf;
   const float *W1 = hp[0], *W2 = hp[3], *Wfc = hp[6];
-  std::vector<float> W1f((size_t)ldf * C1, 0.f), W1t((size_t)C1 * ldf, 0.f), b1(C1), W2c((size_t)kh2 * C1 * C2),
-      Wt2((size_t)kh2 * C2 * C1), b2(C2), Wfcp((size_t)flat * nfc), Wdec((size_t)nfc * ndec * flat), bdec((size_t)ndec * flat);
+  // channel pitch of the activation buffers: 52 floats, so that every row and every time step starts
+  // on a 16-byte boundary (what the TMA-fed GEMM needs); the K index of each weight follows the
+  // same pitch with zero rows at the two pad channels
+  const int C1p = (C1 + 3) / 4 * 4, C2p = (C2 + 3) / 4 * 4, flatp = C2p * h2;
+  m->C1p = C1p; m->C2p = C2p;
+  std::vector<float> W1f((size_t)ldf * C1, 0.f), W1t((size_t)C1 * ldf, 0.f), b1(C1), W2c((size_t)kh2 * C1p * C2, 0.f),
+      Wt2((size_t)kh2 * C2p * C1, 0.f), b2(C2), Wfcp((size_t)flatp * nfc, 0.f), Wdec((size_t)nfc * ndec * flatp, 0.f),
+      bdec((size_t)ndec * flatp, 0.f);
   for (int f = 0; f < C1; ++f)
     for (int b = 0; b < F; ++b) {
       const float v = W1[(size_t)f * F + (F - 1 - b)];  // flip_filters
@@ -261,20 +277,20 @@ static int model_create_dsd(dcs_model* m, int nparams, const float* const* hp, c
     for (int c = 0; c < C1; ++c)
       for (int q = 0; q < kh2; ++q) {
         const float v = W2[((size_t)f * C1 + c) * kh2 + q];
-        W2c[((size_t)(kh2 - 1 - q) * C1 + c) * C2 + f] = v;  // conv2 forward, tap p' = kh2-1-q
-        Wt2[((size_t)q * C2 + f) * C1 + c] = v;              // InverseLayer(conv2)
+        W2c[((size_t)(kh2 - 1 - q) * C1p + c) * C2 + f] = v;  // conv2 forward, tap p' = kh2-1-q
+        Wt2[((size_t)q * C2p + f) * C1 + c] = v;              // InverseLayer(conv2)
       }
   for (int f = 0; f < C2; ++f)
     for (int i = 0; i < h2; ++i)
-      memcpy(&Wfcp[((size_t)i * C2 + f) * nfc], &Wfc[((size_t)f * h2 + i) * nfc], nfc * sizeof(float));
+      memcpy(&Wfcp[((size_t)i * C2p + f) * nfc], &Wfc[((size_t)f * h2 + i) * nfc], nfc * sizeof(float));
   for (int d = 0; d < ndec; ++d) {
     const float* Wd = hp[8 + 2 * d];
     const float* bd = hp[9 + 2 * d];
     for (int f = 0; f < C2; ++f)
       for (int i = 0; i < h2; ++i) {
-        const size_t col = (size_t)d * flat + (size_t)i * C2 + f;
+        const size_t col = (size_t)d * flatp + (size_t)i * C2p + f;
         bdec[col] = bd[f * h2 + i];
-        for (int o = 0; o < nfc; ++o) Wdec[(size_t)o * ndec * flat + col] = Wd[(size_t)o * flat + f * h2 + i];
+        for (int o = 0; o < nfc; ++o) Wdec[(size_t)o * ndec * flatp + col] = Wd[(size_t)o * flat + f * h2 + i];
       }
   }
   std::vector<float> bout(hp[14], hp[14] + 4), bfc(hp[7], hp[7] + nfc);
@@ -286,10 +302,10 @@ static int model_create_dsd(dcs_model* m, int nparams, const float* const* hp, c
     m->dev.push_back(*u.d);
   }
   DCS_TRY(tc_weight_create(W1f.data(), C1, F, C1, &m->tW1f));
-  DCS_TRY(tc_weight_create(W2c.data(), C2, kh2 * C1, C2, &m->tW2c));
-  DCS_TRY(tc_weight_create(Wfcp.data(), nfc, flat, nfc, &m->tWfc));
-  DCS_TRY(tc_weight_create(Wdec.data(), ndec * flat, nfc, ndec * flat, &m->tWdec));
-  DCS_TRY(tc_weight_create(Wt2.data(), C1, kh2 * C2, C1, &m->tWt2));
+  DCS_TRY(tc_weight_create(W2c.data(), C2, kh2 * C1p, C2, &m->tW2c));
+  DCS_TRY(tc_weight_create(Wfcp.data(), nfc, flatp, nfc, &m->tWfc));
+  DCS_TRY(tc_weight_create(Wdec.data(), ndec * flatp, nfc, ndec * flatp, &m->tWdec));
+  DCS_TRY(tc_weight_create(Wt2.data(), C1, kh2 * C2p, C1, &m->tWt2));
   return DCS_OK;
 }
 
@@ -327,6 +343,7 @@ static int run_gemm(dcs_ctx* ctx, const GemmDesc& d, const TcWeight& w, cudaStre
 static int dsd_forward(dcs_ctx* ctx, dcs_model* m, const float* d_mag, const float2* d_X, int64_t T, int64_t ldf,
                        int overlap, int patcher, float2* d_S, int64_t src_stride, cudaStream_t st) {
   const int tc = m->tc, step = tc - overlap, C1 = m->C1, C2 = m->C2, kh2 = m->kh2, h2 = m->h2, nfc = m->nfc;
+  const int C1p = m->C1p, C2p = m->C2p;   // channel pitch of H1 / H2 / the padded decoder activations
   const int64_t P = dcs_num_patches(T, tc, overlap, patcher);
   if (P == 0) {  // clip shorter than one patch: nothing is predicted, every stem is silence
     for (int s = 0; s < m->nsrc; ++s) DCS_CUDA(cudaMemsetAsync(d_S + s * src_stride, 0, (size_t)T * ldf * sizeof(float2), st));
@@ -337,35 +354,36 @@ static int dsd_forward(dcs_ctx* ctx, dcs_model* m, const float* d_mag, const flo
   const int HP = h2 + 2 * (kh2 - 1), ldg = (C1 + 3) / 4 * 4;
   DevBuf &bH1 = ctx->net[0], &bH2 = ctx->net[1], &bz = ctx->net[2], &bap = ctx->net[3], &bG = ctx->net[4];
   const uint64_t sig = ((uint64_t)(DCS_ARCH_DSD + 1) << 48) ^ ((uint64_t)m->F << 24) ^ (uint64_t)(tc * 64);
-  DCS_TRY(ensure_layout(ctx, 0, (size_t)Tp * C1 * 4, sig, st));
-  DCS_TRY(ensure_layout(ctx, 1, (size_t)(Tp - kh2 + 1) * C2 * 4, sig, st));
+  // zero on (re)allocation or layout change; afterwards only the interior (rows and the C of the
+  // Cp channels) is ever written, so the zero padding persists
+  DCS_TRY(ensure_layout(ctx, 0, (size_t)Tp * C1p * 4, sig, st));
+  DCS_TRY(ensure_layout(ctx, 1, (size_t)(Tp - kh2 + 1) * C2p * 4, sig, st));
   DCS_TRY(ensure_layout(ctx, 2, (size_t)P * nfc * 4, sig, st));
-  // zero on (re)allocation or layout change; afterwards only the interior rows are ever written
-  DCS_TRY(ensure_layout(ctx, 3, (size_t)P * 3 * HP * C2 * 4, sig, st));
+  DCS_TRY(ensure_layout(ctx, 3, (size_t)P * 3 * HP * C2p * 4, sig, st));
   DCS_TRY(ensure_layout(ctx, 4, (size_t)P * 3 * tc * ldg * 4, sig, st));
   float *H1 = bH1.as<float>(), *H2 = bH2.as<float>(), *z = bz.as<float>(), *ap = bap.as<float>(), *G = bG.as<float>();
 
   // conv1 + both biases, once per frame (kernel height 1): H1[Tp][C1] = mag[T][F] * W1f
-  GemmDesc g1 = gemm_plain(d_mag, ldf, m->W1f, C1, m->b1, H1, C1, (int)Tp, C1, m->F, 0);
+  GemmDesc g1 = gemm_plain(d_mag, ldf, m->W1f, C1, m->b1, H1, C1p, (int)Tp, C1, m->F, 0);
   g1.a_valid_rows = (int)T;  // util patcher: frames beyond T are zero input
   { ProfScope ps(ctx, "enc_conv1_gemm", st); DCS_TRY(run_gemm(ctx, g1, m->tW1f, st)); }
-  // conv2 + both biases, once per frame offset: rows overlap in H1 (stride C1, length kh2*C1)
-  GemmDesc g2 = gemm_plain(H1, C1, m->W2c, C2, m->b2, H2, C2, (int)(Tp - kh2 + 1), C2, kh2 * C1, 0);
+  // conv2 + both biases, once per frame offset: rows overlap in H1 (stride C1p, length kh2*C1p)
+  GemmDesc g2 = gemm_plain(H1, C1p, m->W2c, C2, m->b2, H2, C2p, (int)(Tp - kh2 + 1), C2, kh2 * C1p, 0);
   { ProfScope ps(ctx, "enc_conv2_gemm", st); DCS_TRY(run_gemm(ctx, g2, m->tW2c, st)); }
-  // bottleneck: patch k reads H2 rows k*step .. k*step+h2-1 (contiguous h2*C2 floats)
-  GemmDesc g3 = gemm_plain(H2, (int64_t)step * C2, m->Wfc, nfc, m->bfc, z, nfc, (int)P, nfc, h2 * C2, 1);
+  // bottleneck: patch k reads H2 rows k*step .. k*step+h2-1 (contiguous h2*C2p floats)
+  GemmDesc g3 = gemm_plain(H2, (int64_t)step * C2p, m->Wfc, nfc, m->bfc, z, nfc, (int)P, nfc, h2 * C2p, 1);
   { ProfScope ps(ctx, "bottleneck_gemm", st); DCS_TRY(run_gemm(ctx, g3, m->tWfc, st)); }
   // three decoder dense layers side by side, scattered into the zero-padded buffer
-  GemmDesc g4 = gemm_plain(z, nfc, m->Wdec, 3 * h2 * C2, m->bdec, ap, (int64_t)3 * HP * C2, (int)P, 3 * h2 * C2, nfc, 1);
-  g4.n_seg = h2 * C2; g4.n_ss = (int64_t)HP * C2; g4.c_col0 = (int64_t)(kh2 - 1) * C2;
+  GemmDesc g4 = gemm_plain(z, nfc, m->Wdec, 3 * h2 * C2p, m->bdec, ap, (int64_t)3 * HP * C2p, (int)P, 3 * h2 * C2p, nfc, 1);
+  g4.n_seg = h2 * C2p; g4.n_ss = (int64_t)HP * C2p; g4.c_col0 = (int64_t)(kh2 - 1) * C2p;
   { ProfScope ps(ctx, "dec_dense_gemm", st); DCS_TRY(run_gemm(ctx, g4, m->tWdec, st)); }
   // InverseLayer(conv2): full correlation on the padded activations, rows (k, d, u)
   // Rows are ordered (u, k, d) -- u-major -- so that a 128-row tile holds one or two output positions
   // u and can skip the taps that only see the zero padding (on average 8 of the 15).
-  GemmDesc g5 = gemm_plain(ap, 0, m->Wt2, C1, nullptr, G, ldg, (int)(P * 3 * tc), C1, kh2 * C2, 0);
-  g5.m_inner = (int)(P * 3); g5.a_so = C2; g5.a_si = (int64_t)HP * C2;
+  GemmDesc g5 = gemm_plain(ap, 0, m->Wt2, C1, nullptr, G, ldg, (int)(P * 3 * tc), C1, kh2 * C2p, 0);
+  g5.m_inner = (int)(P * 3); g5.a_so = C2p; g5.a_si = (int64_t)HP * C2p;
   g5.cm_inner = (int)(P * 3); g5.c_so = ldg; g5.c_si = (int64_t)tc * ldg;
-  g5.kc_rows = (int)(P * 3); g5.kc_unit = C2; g5.kc_pad = kh2 - 1; g5.kc_n = h2; g5.kc_taps = kh2;
+  g5.kc_rows = (int)(P * 3); g5.kc_unit = C2p; g5.kc_pad = kh2 - 1; g5.kc_n = h2; g5.kc_taps = kh2;
   { ProfScope ps(ctx, "dec_convT2_gemm", st); DCS_TRY(run_gemm(ctx, g5, m->tWt2, st)); }
   // InverseLayer(conv1) + bias + ReLU + mask + cross-fade + phase
   DsdMaskArgs a;

@@ -1,5 +1,6 @@
 // common.cuh -- shared helpers for libdcs (sm_100a only).
 #pragma once
+#include <cuda.h>           // CUtensorMap (types only: the encoder is fetched through the runtime)
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -63,6 +64,11 @@ struct dcs_ctx {
   bool debug_simt_gemm = false;
   int tc_acc_mode = 2;
   int tc_debug = 0;
+  int tma_mode = 1;      // DCS_DEBUG_TMA: 0 = register-staged GEMM everywhere, 2 = rewrite the high plane
+  int tma_stages = 2;    // DCS_DEBUG_TMA_STAGES (64-wide tiles: 2 or 4)
+  bool tma_wide = false; // DCS_DEBUG_TMA_WIDE: 128-wide tiles (one CTA per SM) for N > 64
+  int tma_mask = 31;     // DCS_DEBUG_TMA_MASK: which operand views may take the TMA kernel
+  bool tma_sync = false; // DCS_DEBUG_TMA_SYNC: synchronise after each TMA GEMM
   bool debug_smem_fft = false;
   std::vector<dcs_prof_rec> prof;
   // workspace of one in-flight pipeline
@@ -100,9 +106,12 @@ struct ProfScope {
 namespace dcs {
 // weight matrix prepared for the tensor-core path: K-major, zero padded, split for 3xTF32
 struct TcWeight {
-  float* hi = nullptr;
-  float* lo = nullptr;
+  float* hi = nullptr;   // [Np][Kp], K-major, zero padded
+  float* lo = nullptr;   // = hi + Np*Kp (one allocation: the TMA kernel sees the planes stacked)
   int K = 0, N = 0, Kp = 0, Np = 0;
+  // tensor maps over the stacked planes, box = {32, 64, 128} rows x 32 floats; made on first use
+  mutable CUtensorMap tmap[3];
+  mutable bool tmap_ok[3] = {false, false, false};
 };
 }  // namespace dcs
 
@@ -117,6 +126,7 @@ struct dcs_model {
   int arch, F, tc, nsrc;
   // DSD dims
   int C1, C2, kh2, h2, nfc, ndec;
+  int C1p, C2p;   // channel pitch of the activation buffers (multiple of 4 floats)
   int64_t ldw;
   std::vector<float*> dev;  // owned device arrays
   float *W1f, *b1, *W2c, *b2, *Wfc, *bfc, *Wdec, *bdec, *Wt2, *W1t, *bout;
@@ -177,6 +187,9 @@ int launch_gemm(dcs_ctx* ctx, const GemmDesc& d, cudaStream_t st);
 int tc_weight_create(const float* B_rowmajor, int64_t ldb, int K, int N, TcWeight* out);
 void tc_weight_destroy(TcWeight* w);
 int launch_gemm_tc(dcs_ctx* ctx, const GemmDesc& d, const TcWeight& w, cudaStream_t st);
+constexpr int DCS_TMA_FALLBACK = 1;   // launch_gemm_tma: "use the register-staged kernel" (not an error)
+bool gemm_tma_eligible(const GemmDesc& d, int mask);
+int launch_gemm_tma(dcs_ctx* ctx, const GemmDesc& d, const TcWeight& w, cudaStream_t st);
 
 struct DsdMaskArgs {
   const float* G;      // [P][3][tc][ldg]  decoder activations after the transposed conv2

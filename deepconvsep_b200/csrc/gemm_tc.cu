@@ -296,8 +296,8 @@ int tc_weight_create(const float* B, int64_t ldb, int K, int N, TcWeight* out) {
       lo[(size_t)n * Kp + k] = x - h;
     }
   out->K = K; out->N = N; out->Kp = Kp; out->Np = Np;
-  DCS_CUDA(cudaMalloc((void**)&out->hi, hi.size() * sizeof(float)));
-  DCS_CUDA(cudaMalloc((void**)&out->lo, lo.size() * sizeof(float)));
+  DCS_CUDA(cudaMalloc((void**)&out->hi, 2 * hi.size() * sizeof(float)));   // planes stacked: [hi; lo]
+  out->lo = out->hi + hi.size();
   DCS_CUDA(cudaMemcpy(out->hi, hi.data(), hi.size() * sizeof(float), cudaMemcpyHostToDevice));
   DCS_CUDA(cudaMemcpy(out->lo, lo.data(), lo.size() * sizeof(float), cudaMemcpyHostToDevice));
   return DCS_OK;
@@ -305,8 +305,8 @@ int tc_weight_create(const float* B, int64_t ldb, int K, int N, TcWeight* out) {
 
 void tc_weight_destroy(TcWeight* w) {
   if (w->hi) cudaFree(w->hi);
-  if (w->lo) cudaFree(w->lo);
   w->hi = w->lo = nullptr;
+  w->tmap_ok[0] = w->tmap_ok[1] = w->tmap_ok[2] = false;
 }
 
 template <int BN, int STAGES, int AVEC>
@@ -359,6 +359,16 @@ int launch_gemm_tc(dcs_ctx* ctx, const GemmDesc& d, const TcWeight& w, cudaStrea
   if (d.M <= 0 || d.N <= 0) return DCS_OK;
   DCS_REQUIRE(d.K == w.K && d.N == w.N, "tc gemm: weight is %dx%d, GEMM wants K=%d N=%d", w.K, w.N, d.K, d.N);
   DCS_REQUIRE(ceil_div64(d.N, 64) <= 65535, "tc gemm: N=%d too large", d.N);
+  // views the copy engine can describe go to the TMA-fed kernel (gemm_tma.cu), except the skinny
+  // long-K shapes that this file splits over K
+  if (ctx->tma_mode && gemm_tma_eligible(d, ctx->tma_mask)) {
+    const int64_t tiles = ceil_div64(d.M, TC_BM) * ceil_div64(d.N, d.N <= 32 ? 32 : 64);
+    const bool split_k = tiles * 2 <= ctx->num_sms && (d.K + KSTAGE - 1) / KSTAGE >= 16 && d.kc_rows == 0;
+    if (!split_k) {
+      const int r = launch_gemm_tma(ctx, d, w, st);
+      if (r != DCS_TMA_FALLBACK) return r;
+    }
+  }
   // vector width the A view allows: every row start and every segment must keep the alignment
   int avec = 1;
   const bool one_seg = d.k_seg >= d.K;

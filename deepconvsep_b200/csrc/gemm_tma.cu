@@ -1,0 +1,434 @@
+// gemm_tma.cu -- the TMA-fed version of the fp32-accurate tensor-core GEMM (gemm_tc.cu):
+// C = act(A*B + bias) with tcgen05.mma kind::tf32, 3xTF32 split, accumulators in TMEM.
+//
+// gemm_tc.cu stages operands through registers (any strided / segmented view works, but four
+// producer warps per stage spend their time on address arithmetic, the hi/lo split and two
+// shared stores per element).  Here the copy engine does the staging:
+//   warp 5   lane 0: per k-block one cp.async.bulk.tensor.2d for the raw fp32 A tile (128 rows x
+//            32 floats, SWIZZLE_128B = exactly the K-major operand layout of tc.cuh) and two for
+//            the pre-split weight planes; completion is counted on the stage's `full` mbarrier
+//   warps 0-3: when a stage lands, derive the LOW operand plane in shared memory
+//            (lo = x - trunc_tf32(x), elementwise on the swizzled tile: same byte offsets) and
+//            publish it to the async proxy; afterwards the epilogue (thread = output row)
+//   warp 4   lane 0: 3 tcgen05.mma per k-step.  The HIGH A operand is the raw tile itself: the
+//            tf32 datapath reads the top 19 bits of each fp32 word, i.e. trunc_tf32(x)
+//            (checked on the device by tests/test_gpu_gemm.py; DCS_DEBUG_TMA=2 rewrites the
+//            tile with explicitly truncated values instead).
+// A views this kernel takes (everything else stays on gemm_tc.cu):
+//  * "rows" (2-D tensor map): one K segment, offset(m) = (m / m_inner) * a_so + (m % m_inner) * a_si
+//    (plain: m * lda) with a 16-byte aligned row pitch.  Row tiles never straddle two outer
+//    indices u = m / m_inner (the tile grid is [u][ceil(m_inner / 128)]), so a tile is ONE box:
+//    128 rows at column u * a_so + k.  This is InverseLayer(conv2) of the DSD100 net on the
+//    zero-padded decoder activations (examples/dsd100/separate_dsd.py:214-217): u = output time
+//    position, a_so = one time step; overlapping rows (pitch < K) are its conv2 / bottleneck.
+//  * "conv" (4-D tensor map {32 channels, positions, time, patch x decoder}): the 2-D convolutions
+//    of the 30-channel nets on channel-padded NHWC activations (examples/ikala/separate_ikala.py:
+//    177,186-187; examples/bach10/separate_bach10.py:200,209-246).  One k-block = one filter tap
+//    (q, w): the box {32, 128 positions, 1, 1} at (0, pos0 + w, u + q, kd) -- implicit GEMM, no
+//    im2col and no per-row address arithmetic anywhere.
+// Rows / positions / taps outside the tensor are zero-filled by the TMA unit.
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace dcs {
+
+using namespace tc;
+
+constexpr int TM_BM = 128;
+constexpr int TM_SPLIT_WARPS = 4;
+constexpr int TM_MMA_WARP = 4, TM_TMA_WARP = 5;
+constexpr int TM_THREADS = 6 * 32;
+
+template <int BN, int STAGES>
+struct TmSmem {
+  static constexpr int A_BYTES = TM_BM * ROW_BYTES;  // 16 KB
+  static constexpr int B_BYTES = BN * ROW_BYTES;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // A raw(=hi), A lo, B hi, B lo
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+};
+
+struct TmaGemmArgs {
+  int conv;           // 0: rows mode (2-D map), 1: conv mode (4-D map)
+  // A tile = the box {32, pb, tb, kdb} of the map: tile row = pos + pb * (tl + tb * kdl), at most 128.
+  // rows mode and wide conv layers: pb = 128, tb = kdb = 1; narrow conv layers (iKala: 40 / 21
+  // positions) pack several planes (decoder) or several output times (encoder) into one tile
+  int pb, tb, kdb;
+  int n_pos;          // rows per (u, kd): positions (conv) / m_inner (rows mode; plain GEMM: M)
+  int n_u, n_kd;      // output time positions; (patch, decoder) planes (1 outside the decoders)
+  int tiles_pos;      // ceil(n_pos / pb)
+  int col_per_u;      // rows mode: a_so (plain GEMM: 0)
+  int kw;             // conv mode: filter taps along the position axis (k-blocks per time tap)
+  int m_inner;        // row index m = u * m_inner + kd * n_pos + pos
+  int Np;             // row offset of the low weight plane in the stacked weight tensor
+  int acc_mode;
+  int rewrite_hi;     // store trunc_tf32(x) over the raw tile (bring-up cross-check)
+  int cvec;           // C rows allow 16-byte stores
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TM_THREADS)
+gemm_tma_kernel(const GemmDesc d, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const TmaGemmArgs g) {
+  using SM = TmSmem<BN, STAGES>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFF);   // TMA landed
+  uint64_t* split = full + STAGES;                                     // low plane written
+  uint64_t* empty = split + STAGES;                                    // MMAs of the stage retired
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_kdg = (g.n_kd + g.kdb - 1) / g.kdb;
+  const int per_u = g.tiles_pos * n_kdg;
+  const int ug = blockIdx.x / per_u;
+  const int kdg = (blockIdx.x - ug * per_u) / g.tiles_pos;
+  const int u = ug * g.tb, kd = kdg * g.kdb;                                   // first output time / plane of the tile
+  const int r0 = (blockIdx.x - ug * per_u - kdg * g.tiles_pos) * g.pb;       // first position / row
+  const int n0 = blockIdx.y * BN;
+  const uint32_t a_tx = (uint32_t)(g.pb * g.tb * g.kdb) * ROW_BYTES;         // bytes one A box delivers
+  int kb_lo = 0, kb_hi = (d.K + KSTAGE - 1) / KSTAGE;
+  if (d.kc_rows > 0) {   // taps that only see the zero padding are skipped (GemmDesc)
+    const int q_lo = max(0, d.kc_pad - u), q_hi = min(d.kc_taps - 1, d.kc_pad + d.kc_n - 1 - u);
+    kb_lo = (d.kc_unit * q_lo) / KSTAGE;
+    kb_hi = min(kb_hi, (d.kc_unit * (q_hi + 1) + KSTAGE - 1) / KSTAGE);
+    if (kb_hi <= kb_lo) kb_hi = kb_lo + 1;
+  }
+  const int num_kb = kb_hi - kb_lo;
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&split[s], TM_SPLIT_WARPS * 32);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == TM_TMA_WARP && lane == 0) {
+    prefetch_tensormap(&tmA);
+    prefetch_tensormap(&tmB);
+  }
+  constexpr uint32_t TMEM_COLS = 4 * BN;
+  const int n_main = g.acc_mode == 2 ? 3 : 1;
+  const int corr_acc = g.acc_mode == 0 ? 0 : n_main;
+  const int n_main_used = min(n_main, num_kb * (KSTAGE / 8));
+  if (warp == TM_MMA_WARP) tmem_alloc(tmem_slot, TMEM_COLS);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == TM_TMA_WARP) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------- copy engine
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        mbar_wait(&empty[s], ((kb / STAGES) & 1) ^ 1);
+        uint8_t* st = smem + s * SM::STAGE_BYTES;
+        const int k0 = (kb_lo + kb) * KSTAGE;
+        mbar_arrive_expect_tx(&full[s], a_tx + 2 * SM::B_BYTES);
+        if (g.conv) {
+          const int q = (kb_lo + kb) / g.kw, w = (kb_lo + kb) - q * g.kw;
+          tma_load_4d(st, &tmA, &full[s], 0, r0 + w, u + q, kd);
+        } else {
+          tma_load_2d(st, &tmA, &full[s], u * g.col_per_u + k0, r0);
+        }
+        tma_load_2d(st + 2 * SM::A_BYTES, &tmB, &full[s], k0, n0);
+        tma_load_2d(st + 2 * SM::A_BYTES + SM::B_BYTES, &tmB, &full[s], k0, g.Np + n0);
+      }
+    }
+  } else if (warp == TM_MMA_WARP) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------- MMA issuer
+      constexpr uint32_t idesc = make_idesc_tf32(TM_BM, BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t par = (kb / STAGES) & 1;
+        mbar_wait(&full[s], par);
+        mbar_wait(&split[s], par);
+        fence_after_sync();
+        const uint32_t a_hi = smem_u32(smem + s * SM::STAGE_BYTES);
+        const uint32_t a_lo = a_hi + SM::A_BYTES;
+        const uint32_t b_hi = a_hi + 2 * SM::A_BYTES;
+        const uint32_t b_lo = b_hi + SM::B_BYTES;
+#pragma unroll
+        for (int j = 0; j < KSTAGE / 8; ++j) {
+          const uint64_t dah = make_desc(a_hi + KSTEP_BYTES * j), dal = make_desc(a_lo + KSTEP_BYTES * j);
+          const uint64_t dbh = make_desc(b_hi + KSTEP_BYTES * j), dbl = make_desc(b_lo + KSTEP_BYTES * j);
+          const int ks = kb * (KSTAGE / 8) + j;
+          const int ma = ks % n_main;
+          umma_tf32(tmem_base + corr_acc * BN, dal, dbh, idesc, ks != 0);
+          umma_tf32(tmem_base + corr_acc * BN, dah, dbl, idesc, 1);
+          umma_tf32(tmem_base + ma * BN, dah, dbh, idesc, corr_acc == 0 ? 1 : (ks >= n_main));
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    // ------------------------------------------------------------------ low-plane writers
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int s = kb % STAGES;
+      mbar_wait(&full[s], (kb / STAGES) & 1);
+      float4* raw = reinterpret_cast<float4*>(smem + s * SM::STAGE_BYTES);
+      float4* lo = reinterpret_cast<float4*>(smem + s * SM::STAGE_BYTES + SM::A_BYTES);
+      constexpr int CHUNKS = SM::A_BYTES / 16 / (TM_SPLIT_WARPS * 32);   // 8 per thread
+      float4 x[CHUNKS];
+#pragma unroll
+      for (int i = 0; i < CHUNKS; ++i) x[i] = raw[i * (TM_SPLIT_WARPS * 32) + tid];
+#pragma unroll
+      for (int i = 0; i < CHUNKS; ++i) {
+        float4 h, l;
+        split4(x[i], h, l);
+        lo[i * (TM_SPLIT_WARPS * 32) + tid] = l;
+        if (g.rewrite_hi) raw[i * (TM_SPLIT_WARPS * 32) + tid] = h;
+      }
+      fence_proxy_async();
+      mbar_arrive(&split[s]);
+    }
+    // ------------------------------------------------------------------ epilogue
+    // tile row -> (position, output time, plane) -> GEMM row index
+    const int pos = r0 + tid % g.pb, t2 = tid / g.pb, tl = t2 % g.tb, kdl = t2 / g.tb;
+    const int64_t m64 = (int64_t)(u + tl) * g.m_inner + (int64_t)(kd + kdl) * g.n_pos + pos;
+    const bool m_ok = kdl < g.kdb && kd + kdl < g.n_kd && u + tl < g.n_u && pos < g.n_pos && m64 < d.M;
+    const int m = m_ok ? (int)m64 : 0;
+    mbar_wait_relaxed(tmem_full, 0);
+    fence_after_sync();
+    const int64_t roff = (int64_t)(m / d.cm_inner) * d.c_so + (int64_t)((m % d.cm_inner) / d.cm_inner2) * d.c_si +
+                         (int64_t)(m % d.cm_inner2) * d.c_s2 + d.c_col0;
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+    for (int j = 0; j < BN / 16; ++j) {
+      if (n0 + 16 * j >= d.N) break;  // warp-uniform
+      float v[16];
+      tmem_ld16(taddr + 16 * j, v);
+      for (int a = 1; a < n_main_used; ++a) {
+        float w[16];
+        tmem_ld16(taddr + a * BN + 16 * j, w);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += w[i];
+      }
+      if (corr_acc) {
+        float w[16];
+        tmem_ld16(taddr + corr_acc * BN + 16 * j, w);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] += w[i];
+      }
+      if (m_ok) {
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          const int n = n0 + 16 * j + 4 * i4;
+          float x[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            x[e] = v[4 * i4 + e];
+            if (d.bias && n + e < d.N) x[e] += __ldg(d.bias + n + e);
+            if (d.relu) x[e] = fmaxf(x[e], 0.f);
+          }
+          if (g.cvec && n + 4 <= d.N) {   // a group of 4 columns never straddles a C segment (launcher)
+            *reinterpret_cast<float4*>(d.C + roff + (int64_t)(n / d.n_seg) * d.n_ss + (n % d.n_seg)) = make_float4(x[0], x[1], x[2], x[3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (n + e < d.N) d.C[roff + (int64_t)((n + e) / d.n_seg) * d.n_ss + ((n + e) % d.n_seg)] = x[e];
+          }
+        }
+      }
+    }
+    fence_before_sync();
+  }
+  __syncthreads();
+  if (warp == TM_MMA_WARP) {
+    fence_after_sync();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  // the driver entry point is fetched through the runtime: libdcs.so links cudart statically and
+  // does not link libcuda
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// fp32 tensor of `rank` dimensions (dims[0] innermost, strides in BYTES for dims 1..), box = 32
+// floats x box_rows along dim 1 x box2 x box3, 128-byte swizzle, zero fill outside
+static int encode_map(CUtensorMap* map, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      uint32_t box_rows, bool quiet, uint32_t box2 = 1, uint32_t box3 = 1) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  DCS_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+  cuuint64_t gd[4], gs[3];
+  cuuint32_t box[4] = {(cuuint32_t)KSTAGE, box_rows, box2, box3}, estr[4] = {1, 1, 1, 1};
+  for (int i = 0; i < rank; ++i) gd[i] = dims[i];
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), gd, gs, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS && quiet) return DCS_ECUDA;
+  DCS_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu pitch %llu box %u", (int)r, rank,
+              (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)strides_bytes[0], box_rows);
+  return DCS_OK;
+}
+
+// Overlapping rows (pitch < K: a convolution over time read in place) make a tensor whose row
+// pitch is smaller than its row extent.  The copy engine only does address arithmetic and a
+// per-dimension bounds check, so it works; should a driver refuse to encode such a map, the GEMM
+// stays on the register-staged kernel (remembered here).
+static bool g_overlap_rejected = false;
+
+// how the copy engine can address the A view of `d`
+struct TmaView {
+  int mode = 0;                 // 0: not at all, 1: rows (2-D), 2: conv (4-D)
+  int kind = 0;                 // bring-up mask bit (DCS_DEBUG_TMA_MASK)
+  int rows_per_u = 0, n_u = 1, col_per_u = 0, n_kd = 1, kw = 1;
+  int pb = TM_BM, tb = 1, kdb = 1;   // A box (TmaGemmArgs)
+  int rank = 2;
+  uint64_t dims[4] = {1, 1, 1, 1}, strides[3] = {0, 0, 0};
+  bool overlap = false;
+};
+
+static TmaView classify(const GemmDesc& d) {
+  TmaView v;
+  if ((uintptr_t)d.A % 16 != 0 || d.M <= 0) return v;
+  if (d.k_seg >= d.K) {                                   // ---- rows mode
+    if (d.m_inner2 != 1) return v;
+    const bool plain = d.m_inner == 1;
+    const int64_t pitch = plain ? d.a_so : d.a_si;
+    if (pitch <= 0 || pitch % 4 != 0) return v;
+    if (plain) {
+      v.overlap = pitch < d.K;
+      if (v.overlap && g_overlap_rejected) return v;
+      v.kind = v.overlap ? 8 : (d.a_valid_rows < d.M ? 2 : 1);
+      v.rows_per_u = d.M;
+      v.dims[0] = (uint64_t)d.K; v.dims[1] = (uint64_t)std::min(d.M, d.a_valid_rows);
+    } else {
+      if (d.a_valid_rows < d.M || (d.kc_rows != 0 && d.kc_rows != d.m_inner)) return v;
+      v.n_u = (int)ceil_div64(d.M, d.m_inner);
+      if ((int64_t)(v.n_u - 1) * d.a_so + d.K > pitch) return v;       // every row stays inside its pitch
+      v.kind = 4;
+      v.rows_per_u = d.m_inner; v.col_per_u = (int)d.a_so;
+      v.dims[0] = (uint64_t)pitch; v.dims[1] = (uint64_t)std::min<int64_t>(d.m_inner, d.M);
+    }
+    v.strides[0] = (uint64_t)pitch * 4;
+    v.mode = 1;
+    return v;
+  }
+  // ---- conv mode: K = taps x 32 channels, one tap per k-block, time tap stride = time step
+  const int64_t pos_stride = d.m_inner2 > 1 ? d.a_s2 : d.a_si;
+  if (d.k_seg % KSTAGE != 0 || d.K % d.k_seg != 0 || d.k_ss != d.a_so || pos_stride != KSTAGE || d.a_so % KSTAGE != 0) return v;
+  if (d.a_valid_rows < d.M || d.m_inner <= 1 || (d.kc_rows != 0 && (d.kc_rows != d.m_inner || d.kc_unit != d.k_seg))) return v;
+  v.n_u = (int)ceil_div64(d.M, d.m_inner);
+  const int taps_t = d.K / d.k_seg;
+  v.kw = d.k_seg / KSTAGE;
+  v.rank = 4;
+  v.dims[0] = KSTAGE;
+  v.dims[1] = (uint64_t)(d.a_so / KSTAGE);                 // positions per time row (padding included)
+  v.strides[0] = KSTAGE * 4;
+  v.strides[1] = (uint64_t)d.a_so * 4;
+  if (d.m_inner2 > 1) {                                    // rows (u, kd, pos): transposed conv on the padded planes
+    if (d.m_inner % d.m_inner2 != 0 || d.a_si % d.a_so != 0) return v;
+    v.rows_per_u = d.m_inner2; v.n_kd = d.m_inner / d.m_inner2;
+    v.dims[2] = (uint64_t)(d.a_si / d.a_so);               // time rows per plane
+    v.dims[3] = (uint64_t)v.n_kd;
+    v.strides[2] = (uint64_t)d.a_si * 4;
+  } else {                                                 // rows (u, pos): forward conv on one long plane
+    v.rows_per_u = d.m_inner; v.n_kd = 1;
+    v.dims[2] = (uint64_t)(v.n_u + taps_t - 1);
+    v.dims[3] = 1;
+    v.strides[2] = v.strides[1] * v.dims[2];
+  }
+  if ((uint64_t)(v.rows_per_u + v.kw - 1) > v.dims[1]) return v;   // taps must stay inside the time row
+  if (v.rows_per_u < TM_BM) {   // narrow layer: fill the 128 tile rows with several planes / output times
+    v.pb = v.rows_per_u;
+    const int group = TM_BM / v.pb;
+    if (d.m_inner2 > 1) v.kdb = std::max(1, std::min(group, v.n_kd));
+    else if (d.kc_rows == 0) v.tb = std::max(1, std::min(group, v.n_u));
+  }
+  v.kind = 16;
+  v.mode = 2;
+  return v;
+}
+
+bool gemm_tma_eligible(const GemmDesc& d, int mask) {
+  const TmaView v = classify(d);
+  return v.mode != 0 && (mask & v.kind);
+}
+
+template <int BN, int STAGES>
+static int launch_tma(dcs_ctx* ctx, const GemmDesc& d, const TcWeight& w, cudaStream_t st) {
+  using SM = TmSmem<BN, STAGES>;
+  static bool attr = false;
+  if (!attr) {
+    DCS_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    attr = true;
+  }
+  constexpr int slot = BN == 32 ? 0 : (BN == 64 ? 1 : 2);
+  if (!w.tmap_ok[slot]) {   // weight planes stacked [hi; lo], each Np x Kp
+    const uint64_t dims[2] = {(uint64_t)w.Kp, (uint64_t)2 * w.Np}, strides[1] = {(uint64_t)w.Kp * 4};
+    DCS_TRY(encode_map(&w.tmap[slot], w.hi, 2, dims, strides, BN, false));
+    w.tmap_ok[slot] = true;
+  }
+  const TmaView v = classify(d);
+  DCS_REQUIRE(v.mode != 0, "tma gemm: operand view not supported");
+  TmaGemmArgs g;
+  g.conv = v.mode == 2;
+  g.pb = v.pb; g.tb = v.tb; g.kdb = v.kdb;
+  g.n_pos = v.rows_per_u;
+  g.n_u = v.n_u; g.n_kd = v.n_kd;
+  g.tiles_pos = (int)ceil_div64(v.rows_per_u, v.pb);
+  g.col_per_u = v.col_per_u;
+  g.kw = v.kw;
+  g.m_inner = d.m_inner == 1 ? d.M : d.m_inner;
+  g.Np = w.Np;
+  g.acc_mode = ctx->tc_acc_mode;
+  g.rewrite_hi = ctx->tma_mode == 2;
+  g.cvec = ((uintptr_t)d.C % 16 == 0) && d.c_so % 4 == 0 && d.c_si % 4 == 0 && d.c_s2 % 4 == 0 && d.c_col0 % 4 == 0 &&
+           (d.n_seg >= d.N || (d.n_seg % 4 == 0 && d.n_ss % 4 == 0));
+  alignas(64) CUtensorMap tmA;
+  if (v.overlap) {
+    if (encode_map(&tmA, d.A, v.rank, v.dims, v.strides, (uint32_t)v.pb, true) != DCS_OK) {
+      g_overlap_rejected = true;
+      return DCS_TMA_FALLBACK;
+    }
+  } else {
+    DCS_TRY(encode_map(&tmA, d.A, v.rank, v.dims, v.strides, (uint32_t)v.pb, false, (uint32_t)v.tb, (uint32_t)v.kdb));
+  }
+  const int64_t gx = ceil_div64(v.n_u, v.tb) * ceil_div64(v.n_kd, v.kdb) * g.tiles_pos;
+  DCS_REQUIRE(gx <= 0x7fffffff, "tma gemm: M=%d too large", d.M);
+  dim3 grid((unsigned)gx, (unsigned)ceil_div64(d.N, BN));
+  gemm_tma_kernel<BN, STAGES><<<grid, TM_THREADS, SM::TOTAL, st>>>(d, tmA, w.tmap[slot], g);
+  DCS_CHECK_LAUNCH();
+  ctx->launches++;
+  if (ctx->tma_sync) {   // bring-up: attribute an asynchronous fault to the launch that caused it
+    const cudaError_t e = cudaStreamSynchronize(st);
+    DCS_REQUIRE(e == cudaSuccess, "tma gemm M=%d N=%d K=%d m_inner=%d a_so=%lld a_si=%lld mode=%d BN=%d: %s", d.M, d.N, d.K,
+                d.m_inner, (long long)d.a_so, (long long)d.a_si, v.mode, BN, cudaGetErrorString(e));
+  }
+  return DCS_OK;
+}
+
+int launch_gemm_tma(dcs_ctx* ctx, const GemmDesc& d, const TcWeight& w, cudaStream_t st) {
+  if (d.M <= 0 || d.N <= 0) return DCS_OK;
+  DCS_REQUIRE(d.K == w.K && d.N == w.N, "tma gemm: weight is %dx%d, GEMM wants K=%d N=%d", w.K, w.N, d.K, d.N);
+  if (d.N > 64 && ctx->tma_wide) return launch_tma<128, 3>(ctx, d, w, st);
+  if (d.N <= 32) return ctx->tma_stages == 4 ? launch_tma<32, 4>(ctx, d, w, st) : launch_tma<32, 2>(ctx, d, w, st);
+  // two stages = 97 KB and 256 TMEM columns: two CTAs per SM, one's epilogue under the other's main loop
+  return ctx->tma_stages == 4 ? launch_tma<64, 4>(ctx, d, w, st) : launch_tma<64, 2>(ctx, d, w, st);
+}
+
+}  // namespace dcs
