@@ -189,6 +189,7 @@ void tc_weight_destroy(TcWeight* w);
 int launch_gemm_tc(dcs_ctx* ctx, const GemmDesc& d, const TcWeight& w, cudaStream_t st);
 constexpr int DCS_TMA_FALLBACK = 1;   // launch_gemm_tma: "use the register-staged kernel" (not an error)
 bool gemm_tma_eligible(const GemmDesc& d, int mask);
+int launch_splitk_reduce(dcs_ctx* ctx, const GemmDesc& d, const float* partial, int ldp, int k_splits, cudaStream_t st);
 int launch_gemm_tma(dcs_ctx* ctx, const GemmDesc& d, const TcWeight& w, cudaStream_t st);
 
 struct DsdMaskArgs {

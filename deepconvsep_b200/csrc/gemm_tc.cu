@@ -279,6 +279,14 @@ __global__ void splitk_reduce_kernel(const GemmDesc d, const float* __restrict__
   d.C[roff + (int64_t)(n / d.n_seg) * d.n_ss + (n % d.n_seg)] = x;
 }
 
+int launch_splitk_reduce(dcs_ctx* ctx, const GemmDesc& d, const float* partial, int ldp, int k_splits, cudaStream_t st) {
+  const int64_t tot = (int64_t)d.M * d.N;
+  splitk_reduce_kernel<<<(unsigned)ceil_div64(tot, 256), 256, 0, st>>>(d, partial, ldp, k_splits);
+  DCS_CHECK_LAUNCH();
+  ctx->launches++;
+  return DCS_OK;
+}
+
 // ---- host side ------------------------------------------------------------------------------
 int tc_weight_create(const float* B, int64_t ldb, int K, int N, TcWeight* out) {
   // B[k][n] row-major (ld = ldb) -> K-major Bt[n][k], zero padded to Np x Kp, split hi/lo
@@ -359,15 +367,10 @@ int launch_gemm_tc(dcs_ctx* ctx, const GemmDesc& d, const TcWeight& w, cudaStrea
   if (d.M <= 0 || d.N <= 0) return DCS_OK;
   DCS_REQUIRE(d.K == w.K && d.N == w.N, "tc gemm: weight is %dx%d, GEMM wants K=%d N=%d", w.K, w.N, d.K, d.N);
   DCS_REQUIRE(ceil_div64(d.N, 64) <= 65535, "tc gemm: N=%d too large", d.N);
-  // views the copy engine can describe go to the TMA-fed kernel (gemm_tma.cu), except the skinny
-  // long-K shapes that this file splits over K
+  // views the copy engine can describe go to the TMA-fed kernel (gemm_tma.cu)
   if (ctx->tma_mode && gemm_tma_eligible(d, ctx->tma_mask)) {
-    const int64_t tiles = ceil_div64(d.M, TC_BM) * ceil_div64(d.N, d.N <= 32 ? 32 : 64);
-    const bool split_k = tiles * 2 <= ctx->num_sms && (d.K + KSTAGE - 1) / KSTAGE >= 16 && d.kc_rows == 0;
-    if (!split_k) {
-      const int r = launch_gemm_tma(ctx, d, w, st);
-      if (r != DCS_TMA_FALLBACK) return r;
-    }
+    const int r = launch_gemm_tma(ctx, d, w, st);
+    if (r != DCS_TMA_FALLBACK) return r;
   }
   // vector width the A view allows: every row start and every segment must keep the alignment
   int avec = 1;

@@ -64,6 +64,9 @@ struct TmaGemmArgs {
   int acc_mode;
   int rewrite_hi;     // store trunc_tf32(x) over the raw tile (bring-up cross-check)
   int cvec;           // C rows allow 16-byte stores
+  int k_splits;       // > 1: blockIdx.z owns a slice of the k-blocks and stores raw partial sums
+  int ldp;            // row pitch of the partial-sum workspace
+  float* partial;
 };
 
 template <int BN, int STAGES>
@@ -94,6 +97,11 @@ gemm_tma_kernel(const GemmDesc d, const __grid_constant__ CUtensorMap tmA, const
     kb_lo = (d.kc_unit * q_lo) / KSTAGE;
     kb_hi = min(kb_hi, (d.kc_unit * (q_hi + 1) + KSTAGE - 1) / KSTAGE);
     if (kb_hi <= kb_lo) kb_hi = kb_lo + 1;
+  }
+  if (g.k_splits > 1) {   // the launcher sizes the slices so that none is empty
+    const int per = (kb_hi - kb_lo + g.k_splits - 1) / g.k_splits;
+    kb_lo += blockIdx.z * per;
+    kb_hi = min(kb_hi, kb_lo + per);
   }
   const int num_kb = kb_hi - kb_lo;
 
@@ -147,21 +155,28 @@ gemm_tma_kernel(const GemmDesc d, const __grid_constant__ CUtensorMap tmA, const
         const int s = kb % STAGES;
         const uint32_t par = (kb / STAGES) & 1;
         mbar_wait(&full[s], par);
-        mbar_wait(&split[s], par);
         fence_after_sync();
         const uint32_t a_hi = smem_u32(smem + s * SM::STAGE_BYTES);
         const uint32_t a_lo = a_hi + SM::A_BYTES;
         const uint32_t b_hi = a_hi + 2 * SM::A_BYTES;
         const uint32_t b_lo = b_hi + SM::B_BYTES;
+        // the two products that only need what the copy engine delivered go first; the one with
+        // the derived low plane of A follows when the writers are done (off the critical path)
 #pragma unroll
         for (int j = 0; j < KSTAGE / 8; ++j) {
-          const uint64_t dah = make_desc(a_hi + KSTEP_BYTES * j), dal = make_desc(a_lo + KSTEP_BYTES * j);
+          const uint64_t dah = make_desc(a_hi + KSTEP_BYTES * j);
           const uint64_t dbh = make_desc(b_hi + KSTEP_BYTES * j), dbl = make_desc(b_lo + KSTEP_BYTES * j);
           const int ks = kb * (KSTAGE / 8) + j;
           const int ma = ks % n_main;
-          umma_tf32(tmem_base + corr_acc * BN, dal, dbh, idesc, ks != 0);
-          umma_tf32(tmem_base + corr_acc * BN, dah, dbl, idesc, 1);
+          umma_tf32(tmem_base + corr_acc * BN, dah, dbl, idesc, ks != 0);
           umma_tf32(tmem_base + ma * BN, dah, dbh, idesc, corr_acc == 0 ? 1 : (ks >= n_main));
+        }
+        mbar_wait(&split[s], par);
+        fence_after_sync();
+#pragma unroll
+        for (int j = 0; j < KSTAGE / 8; ++j) {
+          const uint64_t dal = make_desc(a_lo + KSTEP_BYTES * j), dbh = make_desc(b_hi + KSTEP_BYTES * j);
+          umma_tf32(tmem_base + corr_acc * BN, dal, dbh, idesc, 1);
         }
         umma_commit(&empty[s]);
       }
@@ -216,7 +231,12 @@ gemm_tma_kernel(const GemmDesc d, const __grid_constant__ CUtensorMap tmA, const
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] += w[i];
       }
-      if (m_ok) {
+      if (m_ok && g.k_splits > 1) {   // raw partial sums; splitk_reduce adds bias / activation
+        float4* dst = reinterpret_cast<float4*>(g.partial + ((int64_t)blockIdx.z * d.M + m) * g.ldp + n0 + 16 * j);
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4)
+          if (n0 + 16 * j + 4 * i4 < g.ldp) dst[i4] = make_float4(v[4 * i4], v[4 * i4 + 1], v[4 * i4 + 2], v[4 * i4 + 3]);
+      } else if (m_ok) {
 #pragma unroll
         for (int i4 = 0; i4 < 4; ++i4) {
           const int n = n0 + 16 * j + 4 * i4;
@@ -410,10 +430,31 @@ static int launch_tma(dcs_ctx* ctx, const GemmDesc& d, const TcWeight& w, cudaSt
   }
   const int64_t gx = ceil_div64(v.n_u, v.tb) * ceil_div64(v.n_kd, v.kdb) * g.tiles_pos;
   DCS_REQUIRE(gx <= 0x7fffffff, "tma gemm: M=%d too large", d.M);
-  dim3 grid((unsigned)gx, (unsigned)ceil_div64(d.N, BN));
+  const int64_t tiles = gx * ceil_div64(d.N, BN);
+  // fewer tiles than CTA slots (two per SM) and a long K: split K so that every SM has work
+  // (conv1 / conv2 of the DSD100 net: 122 tiles of 25-33 k-blocks); fixed-order reduction
+  int splits = 1;
+  const int num_kb = (d.K + KSTAGE - 1) / KSTAGE;
+  if (d.kc_rows == 0 && tiles < 2 * ctx->num_sms && num_kb >= 8) {
+    splits = (int)std::min<int64_t>(2 * ctx->num_sms / tiles, num_kb / 4);
+    if (splits > 1) {
+      const int per = (num_kb + splits - 1) / splits;
+      splits = (num_kb + per - 1) / per;
+    }
+    if (splits < 2) splits = 1;
+  }
+  g.k_splits = splits;
+  g.ldp = (d.N + 3) / 4 * 4;
+  g.partial = nullptr;
+  if (splits > 1) {
+    DCS_TRY(ctx->net[8].ensure((size_t)splits * d.M * g.ldp * sizeof(float), st));
+    g.partial = ctx->net[8].as<float>();
+  }
+  dim3 grid((unsigned)gx, (unsigned)ceil_div64(d.N, BN), (unsigned)splits);
   gemm_tma_kernel<BN, STAGES><<<grid, TM_THREADS, SM::TOTAL, st>>>(d, tmA, w.tmap[slot], g);
   DCS_CHECK_LAUNCH();
   ctx->launches++;
+  if (splits > 1) DCS_TRY(launch_splitk_reduce(ctx, d, g.partial, g.ldp, splits, st));
   if (ctx->tma_sync) {   // bring-up: attribute an asynchronous fault to the launch that caused it
     const cudaError_t e = cudaStreamSynchronize(st);
     DCS_REQUIRE(e == cudaSuccess, "tma gemm M=%d N=%d K=%d m_inner=%d a_so=%lld a_si=%lld mode=%d BN=%d: %s", d.M, d.N, d.K,

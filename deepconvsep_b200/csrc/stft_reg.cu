@@ -12,6 +12,7 @@
 //     coalesced, and the window shifts.  No shared accumulator, no atomics: the summation order
 //     is the reference's (ascending frame index) and the result is run-to-run deterministic.
 //     N/hop - 1 halo frames are recomputed at the start of each span.
+#include <stdlib.h>
 #include "common.cuh"
 #include "fft_reg.cuh"
 
@@ -244,9 +245,11 @@ static int launch_istft_reg_t(dcs_stft* p, const float2* d_S, int nsrc, int64_t 
   constexpr int GPC = REG_THREADS / T;
   const int hop = 64 * HS;
   const int64_t num_hops = ceil_div64(Lout, hop);
-  // hops per group: long enough to amortise the N/hop-1 halo frames, short enough to give every
-  // SM several waves of groups
-  const int64_t target_groups = (int64_t)p->ctx->num_sms * 12 * (32 / T) * 2;
+  // hops per group: as long as possible (each group recomputes N/hop-1 halo frames) while every SM
+  // still gets its 12 resident warps: ONE full wave of equal-sized groups (DCS_DEBUG_ISTFT_WAVES=2:
+  // the earlier two-wave split)
+  static const int waves = [] { const char* e = getenv("DCS_DEBUG_ISTFT_WAVES"); return e && e[0] == '2' ? 2 : 1; }();
+  const int64_t target_groups = (int64_t)p->ctx->num_sms * 12 * (32 / T) * waves;
   int64_t hpg = ceil_div64((int64_t)nsrc * num_hops, target_groups);
   if (hpg < 12) hpg = 12;
   if (hpg > 64) hpg = 64;

@@ -15,7 +15,7 @@ if len(sys.argv) > 1:
             a = np.sqrt(6.0/((s[0]+s[1])*s[2]*s[3])) if len(s)==4 else (np.sqrt(6.0/(s[0]+s[1])) if len(s)==2 else 0.1)
             out.append(rng.uniform(-a,a,size=s).astype(np.float32))
         return out
-    tag = "TMA=%s mask=%s stages=%s" % (os.environ.get("DCS_DEBUG_TMA", "1"), os.environ.get("DCS_DEBUG_TMA_MASK", "15"), os.environ.get("DCS_DEBUG_TMA_STAGES", "2") + " narrow=" + os.environ.get("DCS_DEBUG_TMA_NARROW", "0"))
+    tag = "TMA=%s mask=%s stages=%s" % (os.environ.get("DCS_DEBUG_TMA", "1"), os.environ.get("DCS_DEBUG_TMA_MASK", "15"), os.environ.get("DCS_DEBUG_TMA_STAGES", "2") + " istft_waves=" + os.environ.get("DCS_DEBUG_ISTFT_WAVES", "1"))
     if sys.argv[1] == "gemm":
         ctx = Context(0)
         rng = np.random.default_rng(0)
@@ -63,4 +63,4 @@ else:
             return -1
     run({"DCS_DEBUG_TMA": "0"}, "pipe")
     run({}, "pipe")
-    run({"DCS_DEBUG_TMA_NARROW": "1"}, "pipe")
+    run({"DCS_DEBUG_ISTFT_WAVES": "2"}, "pipe")
