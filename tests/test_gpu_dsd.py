@@ -8,7 +8,7 @@ import pytest
 torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
-from oracle import dsp, nets, pipeline, patch  # noqa: E402
+from oracle import dsp, nets, pipeline, patch, bsseval  # noqa: E402
 
 TOL = 1e-4
 # The reference's ratio mask is discontinuous where every rectified source output vanishes
@@ -37,6 +37,17 @@ def sdr(ref, est):
     return 10 * np.log10(np.sum(ref ** 2) / max(np.sum((ref - est) ** 2), 1e-30))
 
 
+def check_bss_eval(got, want, stems):
+    """the reference's own metric (evaluation/bss_eval/bss_eval_sources.m, restated in oracle.bsseval):
+    SDR / SIR / SAR of the GPU stems and of the oracle stems against the true sources differ by
+    <= 0.01 dB and pick the same source ordering"""
+    g = bsseval.bss_eval_sources(got.astype(np.float64), stems)
+    w = bsseval.bss_eval_sources(want, stems)
+    assert list(g[3]) == list(w[3])
+    for name, a, b in zip(("SDR", "SIR", "SAR"), g[:3], w[:3]):
+        assert np.max(np.abs(a - b)) <= 0.01, (name, a, b)
+
+
 def make_sep(N, seed=0, overlap=25, patcher="standalone", window="hanning", hop=512):
     from deepconvsep_b200.engine import Separator
     F = N // 2 + 1
@@ -61,6 +72,8 @@ def test_separate_matches_oracle(N, seconds, overlap, patcher):
     check_stems(got, want, kinks, bound)
     for s in range(4):
         assert abs(sdr(stems[s], got[s]) - sdr(stems[s], want[s])) <= 0.01
+    if (N, seconds) == (1024, 4.0):
+        check_bss_eval(got, want, stems)
     # the device-buffer entry point gives the same bits as the host-buffer one
     d = sep.separate_device(torch.tensor(mix, dtype=torch.float32, device="cuda"))
     assert np.array_equal(d.cpu().numpy(), got)
@@ -135,6 +148,7 @@ def test_medium_clip_parity():
             e = rel(got[s].astype(np.float64), want[s])
             assert e <= TOL, (N, s, e)
             assert abs(sdr(stems[s], got[s]) - sdr(stems[s], want[s])) <= 0.01
+        check_bss_eval(got, want, stems)
 
 
 def test_pcm16_wav_contract():
