@@ -8,6 +8,7 @@ Reference call sites restated here:
   iKala (no pool)    examples/ikala/trainCNN.py:66-110
   Bach10             examples/bach10/separate_bach10.py:172-229 (net), :245-264 (mask)
   Score-informed     examples/bach10_scoreinformed/trainCNNrwc.py:134-193 (net), :248-263 (mask)
+  Stereo / ILD       examples/dsd100_2ch_ILD/trainCNN_ILD_DSD100.py:66-113 (net), :176-189 (mask)
 Lasagne layer semantics: SURVEY.md App. A.2 (Conv2DLayer flips filters; DenseLayer defaults
 to rectify; InverseLayer = gradient of the layer output wrt its input, tied weights).
 """
@@ -31,7 +32,14 @@ ARCHS = {
                    dec_of_out=(0, 1, 2, 3), ndec=4, mask="bach10"),
     "bach10_score": dict(nsrc=4, nch=4, c1=(30, 1, 30, 1, 4), pool=0, c2=(30, "2T/3", 1), nfc=256,
                          dec_of_out=(0, 1, 2, 3), ndec=4, mask="bach10"),
+    # stereo DSD100 with the inter-aural level difference loss: 2 input channels, one decoder per
+    # source, each InverseLayer(conv1) returns both channels -> 8 outputs ordered (source, channel)
+    # (trainCNN_ILD_DSD100.py:88-106); masks are normalised per channel over the sources (:183-186)
+    "dsd_ild": dict(nsrc=4, nch=2, c1=(50, 1, "F", 1, 1), pool=0, c2=(50, "T/2", 1), nfc=256,
+                    dec_of_out=(0, 1, 2, 3), ndec=4, mask="ild"),
 }
+
+EPS_ILD = 1e-12  # trainCNN_ILD_DSD100.py:153
 
 
 def arch_dims(arch, F, tc):
@@ -96,6 +104,8 @@ def infer_arch(params):
         for arch in ("ikala", "ikala_nopool"):
             if arch_dims(arch, 513, 30)["flat"] == wfc[0]:
                 return arch, 513, 30
+    if n == 17 and w1[0] == 50 and w1[1] == 2:
+        return "dsd_ild", w1[3], 2 * w2[2]
     if n == 17 and w1[0] == 30:
         arch = "bach10_score" if w1[1] == 4 else "bach10"
         for F in (2049, 1025, 513):
@@ -230,3 +240,27 @@ def predict_function2(params, x, arch, rand=None):
     # score-informed: mixture estimate = sum of the input channels (trainCNNrwc.py:258)
     mix = x.sum(axis=1, keepdims=True) if a["nch"] > 1 else x[:, 0:1]
     return [m[:, i:i + 1] * mix for i in range(a["nsrc"])]
+
+
+def predict_function_ild(params, x, rand=None):
+    """`predict_function` of the stereo / ILD trainer (trainCNN_ILD_DSD100.py:176-189,232):
+    x [B, 2, tc, F] -> list over the input channels j of [B, nsrc, tc, F] = mask_j * x[:, j].
+    The network's outputs are ordered (source, channel); channel j's masks are outputs j::nch
+    divided by their sum over the sources (+ eps * N(0, 0.1) noise with eps = 1e-12: `rand` None
+    uses the closed form -- an all-zero bin has numerator 0, so its mask is 0 -- and drops the
+    additive eps * noise on the estimate, 1e-13 absolute)."""
+    a = ARCHS["dsd_ild"]
+    x = np.asarray(x, dtype=np.float64)
+    pred = predict(params, x, "dsd_ild")
+    nch, nsrc = a["nch"], a["nsrc"]
+    out = []
+    for j in range(nch):
+        pj = pred[:, j::nch]
+        tot = pj.sum(axis=1, keepdims=True)
+        if rand is not None:
+            mask = pj / (tot + EPS_ILD * rand)
+            out.append(mask * x[:, j:j + 1] + EPS_ILD * rand)
+        else:
+            mask = pj / np.where(tot > 0, tot, 1.0)
+            out.append(mask * x[:, j:j + 1])
+    return out

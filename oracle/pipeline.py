@@ -7,6 +7,7 @@ source.  This is both the parity checker for the CUDA pipeline and the timed CPU
   iKala    examples/ikala/separate_ikala.py:194-256  (hanning, N=1024, overlap 20, L+R)
   Bach10   examples/bach10/separate_bach10.py:232-306 (blackmanharris, N=4096, overlap 25)
   util patcher variant: examples/dsd100/trainCNN.py:300-333
+  stereo / ILD variant: examples/dsd100_2ch_ILD/trainCNN_ILD_DSD100.py:291-327
 """
 import numpy as np
 from . import dsp, patch, nets
@@ -113,6 +114,34 @@ def separate_score(audio, filters, params, frameSize=4096, hopSize=512, window=N
         audio_out = dsp.compute_inverse(mm[i, :len(ph)] / scale_factor, ph, frameSize=frameSize, hopSize=hopSize, window=window)
         stems.append(audio_out[:len(audio)] if len(audio_out) > len(audio) else audio_out)
     return np.stack(stems)
+
+
+def separate_stereo(audio, params, frameSize=1024, hopSize=512, window=np.hanning, scale_factor=0.3,
+                    time_context=30, overlap=25, batch_size=32):
+    """Separation loop of the stereo / ILD trainer (trainCNN_ILD_DSD100.py:299-327):
+    audio float64 [L, 2] -> stems float64 [L, nsrc, 2] (`sep_audio`).  One STFT per channel
+    (`compute_transform`), util's zero-padded patcher on the [2, T, F] tensor, one network pass per
+    batch, then per channel the 4-source cross-fade and one iSTFT per (source, channel) with that
+    channel's mixture phase."""
+    a = nets.ARCHS["dsd_ild"]
+    nch = audio.shape[1]
+    mags, phs = [], []
+    for j in range(nch):                                   # transform.py:105-119
+        m, p = dsp.compute_file(audio[:, j], phase=True, frameSize=frameSize, hopSize=hopSize, window=window)
+        mags.append(m)
+        phs.append(p)
+    mag = scale_factor * np.stack(mags).astype(np.float32)  # :304
+    batches, nchunks = patch.generate_overlapadd_util(mag, input_size=mag.shape[-1], time_context=time_context,
+                                                      overlap=overlap, batch_size=batch_size)
+    output = np.array([nets.predict_function_ild(params, b) for b in batches])   # [nb, nch, B, nsrc, tc, F]
+    sep = np.zeros((audio.shape[0], a["nsrc"], nch))
+    for j in range(nch):
+        mm = patch.overlapadd_multi(np.swapaxes(output[:, j:j + 1], 1, 3), batches, nchunks, overlap=overlap)
+        for i in range(a["nsrc"]):
+            audio_out = dsp.compute_inverse(mm[i, :phs[j].shape[0]] / scale_factor, phs[j], frameSize=frameSize,
+                                            hopSize=hopSize, window=window)
+            sep[:, i, j] = audio_out[:audio.shape[0]]
+    return sep
 
 
 def synth_mixture(seconds, seed, sr=44100):
