@@ -41,6 +41,7 @@ _SIGS = {
     "dcs_separate_spec": (C.c_int, [_p, _p, _p, _p, _i64, _i64, C.c_int, C.c_int, _p, _i64, _p]),
     "dcs_separate_spec_channels": (C.c_int, [_p, _p, _p, _i64, _p, _i64, _i64, C.c_int, C.c_int, _p, _i64, _p]),
     "dcs_separate_audio_score": (C.c_int, [_p, _p, _p, _p, _i64, _p, C.c_float, C.c_int, C.c_int, _p, _i64, _p]),
+    "dcs_xcorr_lags": (C.c_int, [_p, _p, _p, C.c_int, _i64, C.c_int, _p, _p]),
     "dcs_gemm_f32": (C.c_int, [_p, C.c_int, _p, _i64, _p, _i64, _p, _p, _i64, C.c_int, C.c_int, C.c_int, C.c_int, _p]),
     "dcs_separate_audio": (C.c_int, [_p, _p, _p, _p, _i64, C.c_float, C.c_int, C.c_int, _p, _i64, _p]),
     "dcs_separate_host": (C.c_int, [_p, _p, _p, _p, _i64, C.c_float, C.c_int, C.c_int, _p, _i64, _p]),

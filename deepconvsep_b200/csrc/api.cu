@@ -490,6 +490,13 @@ int dcs_gemm_f32(dcs_ctx* ctx, int engine, const float* d_A, int64_t lda, const 
   return r;
 }
 
+int dcs_xcorr_lags(dcs_ctx* ctx, const float* const* h_a, const float* const* h_b, int npairs, int64_t num_samples, int flen,
+                   double* h_out, void* stream) {
+  DCS_REQUIRE(ctx && h_a && h_b && h_out, "dcs_xcorr_lags: NULL argument");
+  DCS_CUDA(cudaSetDevice(ctx->device));
+  return launch_xcorr_lags(ctx, h_a, h_b, npairs, num_samples, flen, h_out, (cudaStream_t)stream);
+}
+
 int dcs_separate_audio(dcs_ctx* ctx, dcs_model* m, dcs_stft* p, const float* d_audio, int64_t L, float scale_factor,
                        int overlap, int patcher, float* d_stems, int64_t stem_stride, void* stream) {
   DCS_REQUIRE(ctx && m && p && d_audio && d_stems, "dcs_separate_audio: NULL argument");

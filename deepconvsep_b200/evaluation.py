@@ -1,0 +1,110 @@
+"""BSS-Eval 3.0 `bss_eval_sources` (evaluation/bss_eval/bss_eval_sources.m; used by
+evaluation/evaluate_SS_iKala.m:58-59 and evaluation/Bach10_eval_only.m:94) with the O(L) work on
+the GPU -- SURVEY.md 8(f) row 3.
+
+The reference decomposes each estimate into s_true + e_spat + e_interf + e_artif with 512-tap
+least-squares projections whose normal equations are made of correlation lags |m| < 512
+(:110-159).  Here
+
+  * libdcs computes every needed lag in float64 on the device (`dcs_xcorr_lags`, csrc/bsseval.cu):
+    source x source (Gram matrix blocks), source x estimate (right-hand sides), estimate energy;
+  * this module assembles the (nsrc*flen)^2 block-Toeplitz Gram matrix, solves it once per
+    estimate (and its diagonal blocks for the single-source projections) and forms the ratios.
+
+No filtering pass is needed: P_j (projection on source j's delays) and P_all (on all sources') are
+orthogonal projections with span_j inside span_all, so with c = G^-1 D
+    |s_true + e_spat|^2 = |P_j se|^2 = c_j.D_j        |e_interf|^2 = |P_all se|^2 - |P_j se|^2
+    |e_artif|^2 = |se|^2 - |P_all se|^2                |e_interf + e_artif|^2 = |se|^2 - |P_j se|^2
+which are the energies of bss_source_crit (:189-199).  The GPU path is mandatory: without libdcs /
+a CUDA device the import of the engine raises (no CPU fallback here; the numpy restatement lives in
+oracle/bsseval.py as test infrastructure)."""
+import ctypes as C
+import itertools
+import numpy as np
+
+from . import _lib
+from .engine import Context, _ptr, _stream_ptr
+
+FLEN = 512
+
+
+def xcorr_lags(ctx, pairs, L, flen=FLEN, stream=None):
+    """pairs: list of (a, b) torch float32 CUDA vectors of L samples -> float64 [npairs, 2*flen-1],
+    out[p, li] = sum_t a[t + li - (flen-1)] * b[t]"""
+    n = len(pairs)
+    pa = (C.c_void_p * n)(*[_ptr(a) for a, _ in pairs])
+    pb = (C.c_void_p * n)(*[_ptr(b) for _, b in pairs])
+    out = np.empty((n, 2 * flen - 1), dtype=np.float64)
+    _lib.check(ctx.lib.dcs_xcorr_lags(ctx.handle, pa, pb, n, int(L), int(flen), out.ctypes.data, _stream_ptr(stream)))
+    return out
+
+
+def _solve(G, D):
+    try:
+        return np.linalg.solve(G, D)
+    except np.linalg.LinAlgError:       # silent / duplicated source (MATLAB warns and carries on)
+        return np.linalg.lstsq(G, D, rcond=None)[0]
+
+
+def pair_list(n):
+    """the signal pairs whose lags the metric needs, as (kind, i, j) with kind 'ss' (true sources i >= j),
+    'se' (true source i, estimate j) or 'ee' (estimate i with itself), and the index of each"""
+    pairs = [("ss", k1, k2) for k1 in range(n) for k2 in range(k1 + 1)]
+    pairs += [("se", k, i) for k in range(n) for i in range(n)]
+    pairs += [("ee", i, i) for i in range(n)]
+    return pairs, {p if p[0] != "ee" else ("ee", p[1]): q for q, p in enumerate(pairs)}
+
+
+def ratios_from_lags(R, idx, n, flen):
+    """host part: Gram matrix, solves, energy ratios and the best ordering from the lag table R
+    [npairs, 2*flen-1] of `pair_list(n)` -> (SDR, SIR, SAR, perm)"""
+    # Gram matrix: block (k1, k2), entry (a, b) = sum_t s_k1[t-a] s_k2[t-b] = R_ss[k1,k2][(b-a) + flen-1]
+    lag = (np.arange(flen)[None, :] - np.arange(flen)[:, None]) + flen - 1
+    G = np.empty((n * flen, n * flen))
+    for k1 in range(n):
+        for k2 in range(k1 + 1):
+            blk = R[idx["ss", k1, k2]][lag]
+            G[k1 * flen:(k1 + 1) * flen, k2 * flen:(k2 + 1) * flen] = blk
+            G[k2 * flen:(k2 + 1) * flen, k1 * flen:(k1 + 1) * flen] = blk.T
+    SDR, SIR, SAR = (np.zeros((n, n)) for _ in range(3))
+    zero = np.float64(0.0)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for jest in range(n):
+            # D[k*flen + a] = sum_t s_k[t-a] se[t] = R_se[k,jest][flen-1-a]
+            D = np.concatenate([R[idx["se", k, jest]][flen - 1::-1] for k in range(n)])
+            e_se = np.float64(R[idx["ee", jest]][flen - 1])
+            p_all = np.float64(_solve(G, D) @ D)
+            for jtrue in range(n):
+                b = slice(jtrue * flen, (jtrue + 1) * flen)
+                p_j = np.float64(_solve(G[b, b], D[b]) @ D[b])
+                SDR[jest, jtrue] = 10 * np.log10(p_j / np.maximum(e_se - p_j, zero))
+                SIR[jest, jtrue] = 10 * np.log10(p_j / np.maximum(p_all - p_j, zero))
+                SAR[jest, jtrue] = 10 * np.log10(p_all / np.maximum(e_se - p_all, zero))
+    best, perm = -np.inf, None
+    for p in itertools.permutations(range(n)):
+        m = np.mean([SIR[p[j], j] for j in range(n)])
+        if m > best:
+            best, perm = m, p
+    perm = np.array(perm)
+    pick = lambda M: np.array([M[perm[j], j] for j in range(n)])
+    return pick(SDR), pick(SIR), pick(SAR), perm
+
+
+def bss_eval_sources(est, ref, flen=FLEN, ctx=None, stream=None):
+    """est, ref: [nsrc, L] float32 CUDA tensors (estimated / true sources) ->
+    (SDR, SIR, SAR, perm) float64 / int arrays of nsrc entries; estimate perm[j] is matched to true
+    source j, the ordering with the best mean SIR (bss_eval_sources.m:54-64)."""
+    import torch
+    if est.shape != ref.shape or est.dim() != 2:
+        raise ValueError("estimated and true sources must both be [nsrc, nsampl]")
+    if not (est.is_cuda and ref.is_cuda and est.dtype == torch.float32 and ref.dtype == torch.float32):
+        raise ValueError("bss_eval_sources takes float32 CUDA tensors")
+    est, ref = est.contiguous(), ref.contiguous()
+    n, L = ref.shape
+    if ctx is None:
+        ctx = Context(ref.device.index or 0)
+    kinds, idx = pair_list(n)
+    sig = {"ss": (ref, ref), "se": (ref, est), "ee": (est, est)}
+    pairs = [(sig[k][0][i], sig[k][1][j]) for k, i, j in kinds]
+    R = xcorr_lags(ctx, pairs, L, flen, stream)
+    return ratios_from_lags(R, idx, n, flen)

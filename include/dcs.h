@@ -150,6 +150,17 @@ int dcs_separate_audio_score(dcs_ctx* ctx, dcs_model* model, dcs_stft* plan, con
 int dcs_gemm_f32(dcs_ctx* ctx, int engine, const float* d_A, int64_t lda, const float* h_B, int64_t ldb,
                  const float* h_bias, float* d_C, int64_t ldc, int M, int N, int K, int relu, void* stream);
 
+/* ---- evaluation: BSS-Eval 3.0 correlation lags ------------------------ */
+/* The O(num_samples) part of evaluation/bss_eval/bss_eval_sources.m: the inner products between
+ * delayed copies of the true sources (:120-136) and between them and an estimate (:138-145), which
+ * the reference takes from FFT cross-correlations and of which only lags |m| < flen (512) are used.
+ * For each pair p of float device signals of num_samples samples:
+ *     h_out[p][li] = sum_t a_p[t + li - (flen-1)] * b_p[t],   li = 0 .. 2*flen-2      (float64)
+ * h_a / h_b: HOST arrays of npairs DEVICE pointers; h_out: HOST double[npairs][2*flen-1].
+ * flen <= 512.  Deterministic (fixed summation order).  Synchronises the stream. */
+int dcs_xcorr_lags(dcs_ctx* ctx, const float* const* h_a, const float* const* h_b, int npairs,
+                   int64_t num_samples, int flen, double* h_out, void* stream);
+
 /* ---- whole train_auto() on device buffers (separate_dsd.py:289-306) ----------------------- */
 /* d_audio float[L] mono in [-1,1] -> d_stems float[nsrc][stem_stride] (first L samples valid) */
 int dcs_separate_audio(dcs_ctx* ctx, dcs_model* model, dcs_stft* plan, const float* d_audio,
