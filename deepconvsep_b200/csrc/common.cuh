@@ -186,6 +186,7 @@ int launch_gemm(dcs_ctx* ctx, const GemmDesc& d, cudaStream_t st);
 
 int tc_weight_create(const float* B_rowmajor, int64_t ldb, int K, int N, TcWeight* out);
 void tc_weight_destroy(TcWeight* w);
+void tc_weight_encode_maps(TcWeight* w);
 int launch_gemm_tc(dcs_ctx* ctx, const GemmDesc& d, const TcWeight& w, cudaStream_t st);
 constexpr int DCS_TMA_FALLBACK = 1;   // launch_gemm_tma: "use the register-staged kernel" (not an error)
 bool gemm_tma_eligible(const GemmDesc& d, int mask);

@@ -308,6 +308,7 @@ int tc_weight_create(const float* B, int64_t ldb, int K, int N, TcWeight* out) {
   out->lo = out->hi + hi.size();
   DCS_CUDA(cudaMemcpy(out->hi, hi.data(), hi.size() * sizeof(float), cudaMemcpyHostToDevice));
   DCS_CUDA(cudaMemcpy(out->lo, lo.data(), lo.size() * sizeof(float), cudaMemcpyHostToDevice));
+  tc_weight_encode_maps(out);
   return DCS_OK;
 }
 

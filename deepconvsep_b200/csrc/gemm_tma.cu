@@ -389,6 +389,17 @@ bool gemm_tma_eligible(const GemmDesc& d, int mask) {
   return v.mode != 0 && (mask & v.kind);
 }
 
+// tensor maps of the stacked [hi; lo] weight planes (each Np x Kp) for the three tile widths, made
+// when the weight is created -- single-threaded -- so that contexts on several host threads can
+// share a model without racing on the lazily filled cache.  A failure here is not an error: the
+// launch path encodes on first use (and reports).
+void tc_weight_encode_maps(TcWeight* w) {
+  const uint64_t dims[2] = {(uint64_t)w->Kp, (uint64_t)2 * w->Np}, strides[1] = {(uint64_t)w->Kp * 4};
+  const uint32_t rows[3] = {32, 64, 128};
+  for (int slot = 0; slot < 3; ++slot)
+    w->tmap_ok[slot] = encode_map(&w->tmap[slot], w->hi, 2, dims, strides, rows[slot], true) == DCS_OK;
+}
+
 template <int BN, int STAGES>
 static int launch_tma(dcs_ctx* ctx, const GemmDesc& d, const TcWeight& w, cudaStream_t st) {
   using SM = TmSmem<BN, STAGES>;
@@ -398,7 +409,7 @@ static int launch_tma(dcs_ctx* ctx, const GemmDesc& d, const TcWeight& w, cudaSt
     attr = true;
   }
   constexpr int slot = BN == 32 ? 0 : (BN == 64 ? 1 : 2);
-  if (!w.tmap_ok[slot]) {   // weight planes stacked [hi; lo], each Np x Kp
+  if (!w.tmap_ok[slot]) {   // normally done by tc_weight_encode_maps at weight creation
     const uint64_t dims[2] = {(uint64_t)w.Kp, (uint64_t)2 * w.Np}, strides[1] = {(uint64_t)w.Kp * 4};
     DCS_TRY(encode_map(&w.tmap[slot], w.hi, 2, dims, strides, BN, false));
     w.tmap_ok[slot] = true;
