@@ -15,7 +15,11 @@ No filtering pass is needed: P_j (projection on source j's delays) and P_all (on
 orthogonal projections with span_j inside span_all, so with c = G^-1 D
     |s_true + e_spat|^2 = |P_j se|^2 = c_j.D_j        |e_interf|^2 = |P_all se|^2 - |P_j se|^2
     |e_artif|^2 = |se|^2 - |P_all se|^2                |e_interf + e_artif|^2 = |se|^2 - |P_j se|^2
-which are the energies of bss_source_crit (:189-199).  The GPU path is mandatory: without libdcs /
+which are the energies of bss_source_crit (:189-199).  `bss_eval_images` / `bss_eval_windowed` are the
+multichannel, windowed variant inlined in evaluation/DSD100_eval_only.m:225-306 (30 s windows every
+15 s, estimate j against source j, regressors = every channel of every source, SDR / ISR / SIR / SAR),
+built from the same device lags with the same identities (plus <P_j se, s_true> = <se, s_true>, s_true
+lying in span_j).  The GPU path is mandatory: without libdcs /
 a CUDA device the import of the engine raises (no CPU fallback here; the numpy restatement lives in
 oracle/bsseval.py as test infrastructure)."""
 import ctypes as C
@@ -108,3 +112,84 @@ def bss_eval_sources(est, ref, flen=FLEN, ctx=None, stream=None):
     pairs = [(sig[k][0][i], sig[k][1][j]) for k, i, j in kinds]
     R = xcorr_lags(ctx, pairs, L, flen, stream)
     return ratios_from_lags(R, idx, n, flen)
+
+
+# ------------------------------------------------------------------------ multichannel images, windowed
+def image_pair_list(nsrc, nchan):
+    """signal pairs for the images variant: regressors r = j * nchan + c (source j, channel c), estimates
+    e = j * nchan + i; kinds 'ss' (r1 >= r2), 'se' (r, e), 'ee' (e, e)"""
+    K = nsrc * nchan
+    pairs = [("ss", a, b) for a in range(K) for b in range(a + 1)]
+    pairs += [("se", r, e) for r in range(K) for e in range(K)]
+    pairs += [("ee", e, e) for e in range(K)]
+    return pairs, {p if p[0] != "ee" else ("ee", p[1]): q for q, p in enumerate(pairs)}
+
+
+def images_from_lags(R, idx, nsrc, nchan, flen):
+    """host part of bss_eval_images (DSD100_eval_only.m:240-306) from the lag table of `image_pair_list`
+    -> (SDR, ISR, SIR, SAR), each [nsrc]"""
+    K = nsrc * nchan
+    lag = (np.arange(flen)[None, :] - np.arange(flen)[:, None]) + flen - 1
+    G = np.empty((K * flen, K * flen))
+    for a in range(K):
+        for b in range(a + 1):
+            blk = R[idx["ss", a, b]][lag]
+            G[a * flen:(a + 1) * flen, b * flen:(b + 1) * flen] = blk
+            G[b * flen:(b + 1) * flen, a * flen:(a + 1) * flen] = blk.T
+    out = np.zeros((4, nsrc))
+    zero = np.float64(0.0)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        for j in range(nsrc):
+            rows = slice(j * nchan * flen, (j + 1) * nchan * flen)          # source j's channels
+            e_se = e_true = cross = p_j = p_all = zero
+            for i in range(nchan):
+                e = j * nchan + i
+                D = np.concatenate([R[idx["se", r, e]][flen - 1::-1] for r in range(K)])
+                e_se = e_se + R[idx["ee", e]][flen - 1]
+                e_true = e_true + R[idx["ss", e, e]][flen - 1]              # |s_j,i|^2
+                cross = cross + D[e * flen]                                 # <se_i, s_j,i>  (delay 0)
+                p_all = p_all + _solve(G, D) @ D
+                p_j = p_j + _solve(G[rows, rows], D[rows]) @ D[rows]
+            out[0, j] = 10 * np.log10(e_true / np.maximum(e_se - 2 * cross + e_true, zero))
+            out[1, j] = 10 * np.log10(e_true / np.maximum(p_j - 2 * cross + e_true, zero))
+            out[2, j] = 10 * np.log10(p_j / np.maximum(p_all - p_j, zero))
+            out[3, j] = 10 * np.log10(p_all / np.maximum(e_se - p_all, zero))
+    return out[0], out[1], out[2], out[3]
+
+
+def window_starts(nsampl, win, ove):
+    """first sample of each window: nwin = floor((nsampl - win + 1 + ove) / ove) (DSD100_eval_only.m:228)"""
+    nwin = int(np.floor((nsampl - win + 1 + ove) / float(ove)))
+    return [k * ove for k in range(max(nwin, 0))]
+
+
+def bss_eval_images(est, ref, flen=FLEN, ctx=None, stream=None):
+    """est, ref: [nsrc, nchan, L] float32 CUDA tensors -> (SDR, ISR, SIR, SAR) of estimate j against source j"""
+    import torch
+    if est.shape != ref.shape or est.dim() != 3:
+        raise ValueError("estimated and true images must both be [nsrc, nchan, nsampl]")
+    if not (est.is_cuda and ref.is_cuda and est.dtype == torch.float32 and ref.dtype == torch.float32):
+        raise ValueError("bss_eval_images takes float32 CUDA tensors")
+    if est.stride(2) != 1 or ref.stride(2) != 1:
+        est, ref = est.contiguous(), ref.contiguous()
+    nsrc, nchan, L = ref.shape
+    if ctx is None:
+        ctx = Context(ref.device.index or 0)
+    kinds, idx = image_pair_list(nsrc, nchan)
+    sig = {"ss": (ref, ref), "se": (ref, est), "ee": (est, est)}
+    pairs = [(sig[k][0][a // nchan, a % nchan], sig[k][1][b // nchan, b % nchan]) for k, a, b in kinds]
+    return images_from_lags(xcorr_lags(ctx, pairs, L, flen, stream), idx, nsrc, nchan, flen)
+
+
+def bss_eval_windowed(est, ref, win, ove, flen=FLEN, ctx=None, stream=None):
+    """`bss_eval(ie, i, win, ove)` of DSD100_eval_only.m:225-239 (the caller uses 30 s / 15 s):
+    [nsrc, nchan, L] float32 CUDA tensors -> four float64 arrays [nsrc, nwin]"""
+    starts = window_starts(ref.shape[-1], win, ove)
+    out = np.zeros((4, ref.shape[0], len(starts)))
+    if ctx is None and starts:
+        ctx = Context(ref.device.index or 0)
+    for k, a in enumerate(starts):
+        r = bss_eval_images(est[:, :, a:a + win], ref[:, :, a:a + win], flen, ctx, stream)
+        for q in range(4):
+            out[q, :, k] = r[q]
+    return out[0], out[1], out[2], out[3]

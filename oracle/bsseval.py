@@ -10,6 +10,11 @@ and evaluation/Bach10_eval_only.m:94; this is what "SDR" means in BASELINE.json'
   bss_decomp_mtifilt  :70-106    estimate = s_true + e_spat + e_interf + e_artif  (flen = 512)
   bss_source_crit     :163-199   SDR / SIR / SAR energy ratios in dB
   bss_eval_sources    :1-66      all (estimate, source) pairs, then the ordering with the best mean SIR
+and the windowed multichannel "images" variant inlined in evaluation/DSD100_eval_only.m:
+  bss_eval            :225-239   30 s windows every 15 s (the caller passes 30*fs, 15*fs, :171-177)
+  bss_eval_images     :240-255   estimate j against source j (no ordering search), 512-tap projection
+  project             :257-295   regressors = every channel of every source, each delayed by 0..511
+  bss_image_crit      :297-306   SDR / ISR / SIR / SAR
 
 PARITY UNPINNED against the MATLAB code itself: there is no MATLAB / Octave (and no mir_eval / museval)
 in this image.  It is pinned instead by tests/test_oracle_bsseval.py: `project` against a brute-force
@@ -115,3 +120,68 @@ def bss_eval_sources(se, s, flen=FLEN):
     perm = np.array(perm)
     pick = lambda M: np.array([M[perm[j], j] for j in range(n)])
     return pick(SDR), pick(SIR), pick(SAR), perm
+
+
+# ------------------------------------------------------------------------ multichannel images, windowed
+def project_images(se, S, flen=FLEN):
+    """se [nchan, L]; S [nsrc, nchan, L] -> projection [nchan, L + flen - 1] of each channel of se on the
+    span of all channels of all sources in S delayed by 0..flen-1 (DSD100_eval_only.m:257-295; regressor
+    order = channel fastest, as MATLAB's reshape of [nsampl, nchan, nsrc])."""
+    se = np.atleast_2d(np.asarray(se, dtype=np.float64))
+    S = np.asarray(S, dtype=np.float64)
+    nsrc, nchan, L = S.shape
+    R = S.reshape(nsrc * nchan, L)                       # row j*nchan + c
+    G, Rf, fftlen = _gram(R, flen)
+    out = np.empty((se.shape[0], L + flen - 1))
+    for i in range(se.shape[0]):
+        C = _solve(G, _rhs(se[i], Rf, fftlen, flen))
+        out[i] = _filter_sum(C.reshape(R.shape[0], flen), R, flen)
+    return out
+
+
+def image_crit(s_true, e_spat, e_interf, e_artif):
+    """(SDR, ISR, SIR, SAR) in dB over all channels (DSD100_eval_only.m:297-306)"""
+    with np.errstate(divide="ignore"):
+        sdr = 10 * np.log10(np.sum(s_true ** 2) / np.sum((e_spat + e_interf + e_artif) ** 2))
+        isr = 10 * np.log10(np.sum(s_true ** 2) / np.sum(e_spat ** 2))
+        sir = 10 * np.log10(np.sum((s_true + e_spat) ** 2) / np.sum(e_interf ** 2))
+        sar = 10 * np.log10(np.sum((s_true + e_spat + e_interf) ** 2) / np.sum(e_artif ** 2))
+    return sdr, isr, sir, sar
+
+
+def bss_eval_images(ie, i, flen=FLEN):
+    """ie, i: [nsrc, nchan, L] estimated / true source images -> (SDR, ISR, SIR, SAR), each [nsrc];
+    estimate j is scored against source j (DSD100_eval_only.m:240-255)."""
+    ie = np.asarray(ie, dtype=np.float64)
+    i = np.asarray(i, dtype=np.float64)
+    if ie.shape != i.shape or i.ndim != 3:
+        raise ValueError("estimated and true images must both be [nsrc, nchan, nsampl]")
+    nsrc, nchan, L = i.shape
+    pad = np.zeros((nchan, flen - 1))
+    out = np.zeros((4, nsrc))
+    for j in range(nsrc):
+        s_true = np.concatenate([i[j], pad], axis=1)
+        e_spat = project_images(ie[j], i[j:j + 1], flen) - s_true
+        e_interf = project_images(ie[j], i, flen) - s_true - e_spat
+        e_artif = np.concatenate([ie[j], pad], axis=1) - s_true - e_spat - e_interf
+        out[:, j] = image_crit(s_true, e_spat, e_interf, e_artif)
+    return out[0], out[1], out[2], out[3]
+
+
+def window_starts(nsampl, win, ove):
+    """first sample of each evaluation window (DSD100_eval_only.m:228,236: nwin = floor((nsampl-win+1+ove)/ove))"""
+    nwin = int(np.floor((nsampl - win + 1 + ove) / float(ove)))
+    return [k * ove for k in range(max(nwin, 0))]
+
+
+def bss_eval_windowed(ie, i, win, ove, flen=FLEN):
+    """`bss_eval(ie, i, win, ove)` of DSD100_eval_only.m:225-239 -> four arrays [nsrc, nwin]"""
+    ie = np.asarray(ie, dtype=np.float64)
+    i = np.asarray(i, dtype=np.float64)
+    starts = window_starts(i.shape[-1], win, ove)
+    out = np.zeros((4, i.shape[0], len(starts)))
+    for k, a in enumerate(starts):
+        r = bss_eval_images(ie[:, :, a:a + win], i[:, :, a:a + win], flen)
+        for q in range(4):
+            out[q, :, k] = r[q]
+    return out[0], out[1], out[2], out[3]
