@@ -106,7 +106,7 @@ def test_stereo_ild_masks_and_pipeline():
     (source, channel), masks normalised per channel, closed form == the seeded-noise graph, and the
     dataset loop of :299-327 gives stems whose per-channel sum is the mixture wherever the masks
     cover it."""
-    from oracle import pipeline, dsp
+    from oracle import pipeline
     rng = np.random.default_rng(7)
     F = 65
     params = nets.make_synthetic_params("dsd_ild", F, seed=2)
