@@ -360,7 +360,15 @@ static int dsd_forward(dcs_ctx* ctx, dcs_model* m, const float* d_mag, const flo
   DCS_TRY(ensure_layout(ctx, 1, (size_t)(Tp - kh2 + 1) * C2p * 4, sig, st));
   DCS_TRY(ensure_layout(ctx, 2, (size_t)P * nfc * 4, sig, st));
   DCS_TRY(ensure_layout(ctx, 3, (size_t)P * 3 * HP * C2p * 4, sig, st));
-  DCS_TRY(ensure_layout(ctx, 4, (size_t)P * 3 * tc * ldg * 4, sig, st));
+  // G: the transposed conv2 output.  For the tensor-core mask kernel it is stored frame-major
+  // ([T][6 slots][3 decoders][ldg], GemmDesc fm_*) so that a group of frames is one TMA box; the FFMA
+  // mask kernel reads the patch-major [P][3][tc][ldg] order.  Unwritten slots must stay zero / finite:
+  // the layout kind is part of the signature, so switching re-zeroes the buffer.
+  DsdMaskArgs a;
+  a.ldg = ldg; a.T = (int)T; a.P = (int)P; a.tc = tc; a.overlap = overlap; a.F = m->F; a.G = nullptr;
+  const bool mask_tc = !ctx->debug_simt_gemm && (tc + step - 1) / step <= 6;
+  const size_t g_rows = mask_tc ? (size_t)T * 6 * 3 : (size_t)P * 3 * tc;
+  DCS_TRY(ensure_layout(ctx, 4, g_rows * ldg * 4, sig ^ (mask_tc ? 0x5a5a : 0), st));
   float *H1 = bH1.as<float>(), *H2 = bH2.as<float>(), *z = bz.as<float>(), *ap = bap.as<float>(), *G = bG.as<float>();
 
   // conv1 + both biases, once per frame (kernel height 1): H1[Tp][C1] = mag[T][F] * W1f
@@ -384,13 +392,16 @@ static int dsd_forward(dcs_ctx* ctx, dcs_model* m, const float* d_mag, const flo
   g5.m_inner = (int)(P * 3); g5.a_so = C2p; g5.a_si = (int64_t)HP * C2p;
   g5.cm_inner = (int)(P * 3); g5.c_so = ldg; g5.c_si = (int64_t)tc * ldg;
   g5.kc_rows = (int)(P * 3); g5.kc_unit = C2p; g5.kc_pad = kh2 - 1; g5.kc_n = h2; g5.kc_taps = kh2;
+  if (mask_tc) { g5.fm_step = step; g5.fm_tc = tc; g5.fm_T = (int)T; g5.fm_slots = 6; g5.fm_ndec = 3; }
   { ProfScope ps(ctx, "dec_convT2_gemm", st); DCS_TRY(run_gemm(ctx, g5, m->tWt2, st)); }
   // InverseLayer(conv1) + bias + ReLU + mask + cross-fade + phase
-  DsdMaskArgs a;
-  a.G = G; a.ldg = ldg; a.W1t = m->W1t; a.ldw = (int)m->ldw; a.bout = m->bout; a.X = d_X; a.S = d_S;
-  a.ldf = ldf; a.src_stride = src_stride; a.T = (int)T; a.P = (int)P; a.tc = tc; a.overlap = overlap; a.F = m->F;
+  a.G = G; a.W1t = m->W1t; a.ldw = (int)m->ldw; a.bout = m->bout; a.X = d_X; a.S = d_S;
+  a.ldf = ldf; a.src_stride = src_stride;
   ProfScope ps(ctx, "dec_convT1_mask_xfade", st);
-  if (!ctx->debug_simt_gemm && dsd_mask_tc_supported(a)) return launch_dsd_mask_tc(ctx, a, st);
+  if (mask_tc) {
+    DCS_REQUIRE(dsd_mask_tc_supported(a), "dsd_forward: tensor-core mask kernel does not take this shape");
+    return launch_dsd_mask_tc(ctx, a, st);
+  }
   return launch_dsd_mask(ctx, a, st);   // FFMA kernel: > 6 patches per frame, or bring-up cross-check
 }
 

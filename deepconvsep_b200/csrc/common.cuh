@@ -179,7 +179,28 @@ struct GemmDesc {
   // non-zero input, so a tile skips the k-blocks outside [kc_unit*q_lo, kc_unit*(q_hi+1)).
   // kc_rows = 0 disables it.  (Pure optimisation: the skipped products are exact zeros.)
   int kc_rows, kc_unit, kc_pad, kc_n, kc_taps;
+  // optional frame-major C rows for the transposed conv2 of the DSD100 net (fm_step > 0): GEMM row
+  // m = (p, k, d) = (frame in patch, patch, decoder), m = p * cm_inner + k * fm_ndec + d, is stored at
+  // row ((t * fm_slots + j) * fm_ndec + d) of C with t = k * fm_step + p the mixture frame and
+  // j = k - k_lo(t) the patch slot (k_lo(t) = first patch covering t) -- the order in which the fused
+  // mask kernel consumes them, so that a group of frames is ONE contiguous box.  Rows with t >= fm_T
+  // are dropped.  c_so is then the row pitch.
+  int fm_step, fm_tc, fm_T, fm_slots, fm_ndec;
 };
+// element offset of row m of C (without the column part); -1: the row is not stored
+__host__ __device__ __forceinline__ int64_t gemm_c_row_offset(const GemmDesc& d, int m) {
+  if (d.fm_step > 0) {
+    const int p = m / d.cm_inner, kd = m - p * d.cm_inner;
+    const int k = kd / d.fm_ndec, dd = kd - k * d.fm_ndec;
+    const int t = k * d.fm_step + p;
+    if (t >= d.fm_T) return -1;
+    const int lo = t - d.fm_tc + 1;
+    const int k_lo = lo > 0 ? (lo + d.fm_step - 1) / d.fm_step : 0;
+    return ((int64_t)((int64_t)t * d.fm_slots + (k - k_lo)) * d.fm_ndec + dd) * d.c_so + d.c_col0;
+  }
+  return (int64_t)(m / d.cm_inner) * d.c_so + (int64_t)((m % d.cm_inner) / d.cm_inner2) * d.c_si +
+         (int64_t)(m % d.cm_inner2) * d.c_s2 + d.c_col0;
+}
 GemmDesc gemm_plain(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C,
                     int64_t ldc, int M, int N, int K, int relu);
 int launch_gemm(dcs_ctx* ctx, const GemmDesc& d, cudaStream_t st);
@@ -190,6 +211,8 @@ void tc_weight_encode_maps(TcWeight* w);
 int launch_gemm_tc(dcs_ctx* ctx, const GemmDesc& d, const TcWeight& w, cudaStream_t st);
 constexpr int DCS_TMA_FALLBACK = 1;   // launch_gemm_tma: "use the register-staged kernel" (not an error)
 bool gemm_tma_eligible(const GemmDesc& d, int mask);
+// fp32 [rows][cols] tensor (row pitch in bytes), box = box_rows x 32 floats, 128-byte swizzle, zero fill
+int tma_encode_2d_f32(CUtensorMap* map, const float* base, uint64_t cols, uint64_t rows, uint64_t pitch_bytes, uint32_t box_rows);
 int launch_splitk_reduce(dcs_ctx* ctx, const GemmDesc& d, const float* partial, int ldp, int k_splits, cudaStream_t st);
 int launch_gemm_tma(dcs_ctx* ctx, const GemmDesc& d, const TcWeight& w, cudaStream_t st);
 

@@ -10,9 +10,13 @@
 //   N = (frame, patch slot, decoder) = 8 x 6 x 3 = 144 columns per tile
 //   K = conv1 filters (50, padded to 56 = 7 k-steps)
 //   A = W1t tile [128 bins][K]  (weights; split hi/lo into shared memory ONCE per CTA)
-//   B = G rows   [144][K]       (decoder activations; loaded, split and staged per tile)
+//   B = G rows   [144][K]       (decoder activations).  The transposed conv2 writes G frame-major
+//       (GemmDesc fm_*: row ((t*6 + slot)*3 + decoder)), so the 144 rows of a group are ONE
+//       contiguous box: two cp.async.bulk.tensor loads (k 0-31, k 32-63; columns >= 52 are the copy
+//       engine's zero fill) deliver the raw fp32 tile = the HIGH operand (the tf32 datapath
+//       truncates), four warps derive the LOW plane in shared memory.
 // Persistent CTAs: a CTA owns one 128-bin tile and a contiguous range of 8-frame groups.
-//   warps 0-15 epilogue | warp 16 MMA issue + TMEM alloc | warps 17-24 B producers
+//   warps 0-15 epilogue | warp 16 MMA issue + TMEM alloc | warp 17 TMA | warps 18-21 low plane
 // (16 epilogue warps: a single warp per scheduler runs the dependent mask arithmetic at
 //  IPC ~0.2 -- measured, profiles/r1_notes.md -- so each scheduler gets four.)
 // Double-buffered B stages and TMEM accumulators: the MMAs of group g+1 overlap the epilogue
@@ -32,31 +36,32 @@ constexpr int MT_COLS = MT_FRAMES * MT_SLOTS * 3;  // 144
 constexpr int MT_C1 = 50;
 constexpr int MT_KSTEPS = 7;             // ceil(50 / 8)
 constexpr int MT_EPI_WARPS = 16;          // 4 per TMEM lane quadrant, 2 frames of a group each
-constexpr int MT_PROD_WARPS = 8;
-constexpr int MT_PROD = MT_PROD_WARPS * 32;             // 256 producer threads
-constexpr int MT_THREADS = (MT_EPI_WARPS + 1 + MT_PROD_WARPS) * 32;  // 800
+constexpr int MT_TMA_WARP = MT_EPI_WARPS + 1;
+constexpr int MT_SPLIT_WARPS = 4;
+constexpr int MT_SPLIT = MT_SPLIT_WARPS * 32;            // 128 low-plane threads
+constexpr int MT_THREADS = (MT_EPI_WARPS + 2 + MT_SPLIT_WARPS) * 32;  // 704
 constexpr int MT_A_SUB = MT_BINS * ROW_BYTES;      // 16 KB: [128][32] fp32
 constexpr int MT_B_SUB = MT_COLS * ROW_BYTES;      // 18 KB: [144][32] fp32
 constexpr int MT_A_BYTES = 4 * MT_A_SUB;           // hi k0-31, hi k32-63, lo k0-31, lo k32-63
 constexpr int MT_B_STAGE = 4 * MT_B_SUB;           // same four planes
 constexpr int MT_BAR_OFF = MT_A_BYTES + 2 * MT_B_STAGE;
-constexpr int MT_TAB_OFF = MT_BAR_OFF + 128;       // int64 source-row offsets of the 144 B rows
-constexpr int MT_XF_OFF = MT_TAB_OFF + 2 * MT_COLS * 8;   // cross-fade coefficient tables, 12 float4 per epilogue warp
+constexpr int MT_XF_OFF = MT_BAR_OFF + 128;        // cross-fade coefficient tables, 12 float4 per epilogue warp
 constexpr int MT_SMEM = MT_XF_OFF + MT_EPI_WARPS * 12 * 16 + 1024;  // + alignment slack
 constexpr uint32_t MT_TMEM_COLS = 512;
 
 __global__ void __launch_bounds__(MT_THREADS, 1)
-dsd_mask_tc_kernel(const DsdMaskArgs a, int groups_per_cta, int num_groups) {
+dsd_mask_tc_kernel(const DsdMaskArgs a, const __grid_constant__ CUtensorMap tmG, const float4* __restrict__ xtab,
+                   int groups_per_cta, int num_groups) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   uint8_t* sA = smem;
   uint8_t* sB = smem + MT_A_BYTES;
-  uint64_t* full_b = reinterpret_cast<uint64_t*>(smem + MT_BAR_OFF);
-  uint64_t* empty_b = full_b + 2;
+  uint64_t* full_b = reinterpret_cast<uint64_t*>(smem + MT_BAR_OFF);   // raw B tile landed
+  uint64_t* split_b = full_b + 2;                                       // low plane written
+  uint64_t* empty_b = split_b + 2;                                      // MMAs of the stage retired
   uint64_t* tmem_full = empty_b + 2;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  int64_t* row_src = reinterpret_cast<int64_t*>(smem + MT_TAB_OFF);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int bin0 = blockIdx.x * MT_BINS;
@@ -66,7 +71,8 @@ dsd_mask_tc_kernel(const DsdMaskArgs a, int groups_per_cta, int num_groups) {
 
   if (tid == 0) {
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&full_b[s], MT_PROD);
+      mbar_init(&full_b[s], 1);
+      mbar_init(&split_b[s], MT_SPLIT);
       mbar_init(&empty_b[s], 1);
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], MT_EPI_WARPS * 32);
@@ -74,6 +80,7 @@ dsd_mask_tc_kernel(const DsdMaskArgs a, int groups_per_cta, int num_groups) {
     fence_barrier_init();
   }
   if (warp == MT_EPI_WARPS) tmem_alloc(tmem_slot, MT_TMEM_COLS);
+  if (warp == MT_TMA_WARP && lane == 0) prefetch_tensormap(&tmG);
   // A tile: thread = bin row (threads 0..127), W1t is [c][bin] so the reads are coalesced over bins
   if (tid < MT_BINS) {
     const int b = bin0 + tid;
@@ -99,68 +106,35 @@ dsd_mask_tc_kernel(const DsdMaskArgs a, int groups_per_cta, int num_groups) {
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp > MT_EPI_WARPS) {
-    // ------------------------------------------------------------------ B producers
-    const int pt = tid - (MT_EPI_WARPS + 1) * 32;  // 0..255
-    // Each group stages 144 rows x 16 chunks of 16 B (13 real, the rest zero) = 9 chunks per
-    // thread: 8 consecutive threads read one row's consecutive chunks (coalesced) and write 8
-    // distinct swizzled slots.  The loads of group g+1 are in flight while group g is split,
-    // stored and consumed; the source-row table is double buffered (one bar.sync per group).
-    constexpr int CPT = MT_COLS * 16 / MT_PROD;  // 9
-    auto build_table = [&](int g, int64_t* tab) {
-      for (int rr = pt; rr < MT_COLS; rr += MT_PROD) {
-        const int f = rr / 18, rem = rr - f * 18, j = rem / 3, d = rem - j * 3;
-        const int t = g * MT_FRAMES + f;
-        int64_t src = -1;
-        if (t < a.T) {
-          int k_lo = t - a.tc + 1;
-          k_lo = k_lo > 0 ? (k_lo + step - 1) / step : 0;
-          int k_hi = t / step;
-          if (k_hi > a.P - 1) k_hi = a.P - 1;
-          const int k = k_lo + j;
-          if (k <= k_hi) src = ((int64_t)(k * 3 + d) * a.tc + (t - k * step)) * a.ldg;
-        }
-        tab[rr] = src;
+  if (warp == MT_TMA_WARP) {
+    // ------------------------------------------------------------------ copy engine
+    if (lane == 0) {
+      for (int g = g_begin; g < g_end; ++g) {
+        const int it = g - g_begin, s = it & 1;
+        mbar_wait(&empty_b[s], ((it >> 1) & 1) ^ 1);
+        uint8_t* st = sB + s * MT_B_STAGE;
+        mbar_arrive_expect_tx(&full_b[s], 2 * MT_B_SUB);
+        tma_load_2d(st, &tmG, &full_b[s], 0, g * MT_COLS);                 // k 0..31 of the group's 144 rows
+        tma_load_2d(st + MT_B_SUB, &tmG, &full_b[s], KSTAGE, g * MT_COLS);  // k 32..63 (>= 52: zero fill)
       }
-    };
-    float4 v[CPT];
-    auto issue_loads = [&](const int64_t* tab) {
-#pragma unroll
-      for (int u = 0; u < CPT; ++u) {
-        const int idx = u * MT_PROD + pt;
-        const int rr = idx >> 4, c4 = idx & 15;
-        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c4 < 13) {
-          const int64_t src = tab[rr];
-          if (src >= 0) v[u] = __ldg(reinterpret_cast<const float4*>(a.G + src) + c4);
-        }
-      }
-    };
-    if (g_begin < g_end) {
-      build_table(g_begin, row_src);
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      issue_loads(row_src);
     }
+  } else if (warp > MT_TMA_WARP) {
+    // ------------------------------------------------------------------ low-plane writers
+    const int pt = tid - (MT_TMA_WARP + 1) * 32;  // 0..127
+    constexpr int CHUNKS = 2 * MT_B_SUB / 16 / MT_SPLIT;   // 18 float4 per thread
     for (int g = g_begin; g < g_end; ++g) {
       const int it = g - g_begin, s = it & 1;
-      if (g + 1 < g_end) build_table(g + 1, row_src + ((it + 1) & 1) * MT_COLS);
-      mbar_wait_relaxed(&empty_b[s], ((it >> 1) & 1) ^ 1);
-      uint8_t* st = sB + s * MT_B_STAGE;
-#pragma unroll
-      for (int u = 0; u < CPT; ++u) {
-        const int idx = u * MT_PROD + pt;
-        const int rr = idx >> 4, c4 = idx & 15;
-        if (c4 == 12) { v[u].z = 0.f; v[u].w = 0.f; }  // columns 50, 51 of the padded G row
-        float4 hi, lo;
-        split4(v[u], hi, lo);
-        const uint32_t off = (c4 >> 3) * MT_B_SUB + tile_off(rr, c4 & 7);
-        *reinterpret_cast<float4*>(st + off) = hi;
-        *reinterpret_cast<float4*>(st + 2 * MT_B_SUB + off) = lo;
+      mbar_wait(&full_b[s], (it >> 1) & 1);
+      const float4* raw = reinterpret_cast<const float4*>(sB + s * MT_B_STAGE);
+      float4* lo = reinterpret_cast<float4*>(sB + s * MT_B_STAGE + 2 * MT_B_SUB);
+#pragma unroll 6
+      for (int u = 0; u < CHUNKS; ++u) {
+        float4 h, l;
+        split4(raw[u * MT_SPLIT + pt], h, l);
+        lo[u * MT_SPLIT + pt] = l;
       }
       fence_proxy_async();
-      mbar_arrive(&full_b[s]);
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // next table complete, this one no longer read
-      if (g + 1 < g_end) issue_loads(row_src + ((it + 1) & 1) * MT_COLS);
+      mbar_arrive(&split_b[s]);
     }
   } else if (warp == MT_EPI_WARPS) {
     // ------------------------------------------------------------------ MMA issuer
@@ -175,11 +149,19 @@ dsd_mask_tc_kernel(const DsdMaskArgs a, int groups_per_cta, int num_groups) {
         fence_after_sync();
         const uint32_t b_hi = smem_u32(sB + s * MT_B_STAGE), b_lo = b_hi + 2 * MT_B_SUB;
         const uint32_t dcol = tmem_base + s * 256;
-        // corrections first (tiny partial sums), then the 7 main products
+        // corrections first (tiny partial sums), then the 7 main products; the correction that needs
+        // only what the copy engine delivered (Alo * Bhi, Bhi = the raw tile) goes before the wait for
+        // the derived low plane
 #pragma unroll
         for (int j = 0; j < MT_KSTEPS; ++j) {
           const uint32_t ao = (j >> 2) * MT_A_SUB + KSTEP_BYTES * (j & 3), bo = (j >> 2) * MT_B_SUB + KSTEP_BYTES * (j & 3);
           umma_tf32(dcol, make_desc(a_lo + ao), make_desc(b_hi + bo), idesc, j != 0);
+        }
+        mbar_wait(&split_b[s], par);
+        fence_after_sync();
+#pragma unroll
+        for (int j = 0; j < MT_KSTEPS; ++j) {
+          const uint32_t ao = (j >> 2) * MT_A_SUB + KSTEP_BYTES * (j & 3), bo = (j >> 2) * MT_B_SUB + KSTEP_BYTES * (j & 3);
           umma_tf32(dcol, make_desc(a_hi + ao), make_desc(b_lo + bo), idesc, 1);
         }
 #pragma unroll
@@ -199,28 +181,14 @@ dsd_mask_tc_kernel(const DsdMaskArgs a, int groups_per_cta, int num_groups) {
     const int b = bin0 + quad * 32 + lane;
     const bool bok = b < a.F;
     const float bo0 = __ldg(a.bout + 0), bo1 = __ldg(a.bout + 1), bo2 = __ldg(a.bout + 2), bo3 = __ldg(a.bout + 3);
-    const float inv_ov1 = a.overlap > 1 ? 1.0f / (float)(a.overlap - 1) : 0.f;
     float4* xf = reinterpret_cast<float4*>(smem + MT_XF_OFF) + warp * 12;
     for (int g = g_begin; g < g_end; ++g) {
       const int it = g - g_begin, s = it & 1;
       const int tA = g * MT_FRAMES + 2 * fsub;
-      // cross-fade coefficients of this warp's 2 frames x 6 patch slots, one per lane 0..11:
+      // cross-fade coefficients of this warp's 2 frames x 6 patch slots (dsd_xfade_table_kernel):
       // acc <- down*acc + up*mask, (up, down) = (1, 0) for the first covering patch, the linspace
       // ramp for later ones, (0, 1) for empty slots -- the evaluation below is branch free
-      if (lane < 12) {
-        const int ff = lane / 6, j = lane - 6 * ff, t = tA + ff;
-        int k_lo = t - a.tc + 1;
-        k_lo = k_lo > 0 ? (k_lo + step - 1) / step : 0;
-        int k_hi = t / step;
-        if (k_hi > a.P - 1) k_hi = a.P - 1;
-        float up = 0.f, down = 1.f;
-        if (t < a.T && k_lo + j <= k_hi) {
-          const int p = t - (k_lo + j) * step;
-          up = j == 0 ? 1.f : (float)p * inv_ov1;
-          down = j == 0 ? 0.f : (float)(a.overlap - 1 - p) * inv_ov1;
-        }
-        xf[lane] = make_float4(up, down, 0.25f * up, 0.f);
-      }
+      if (lane < 12) xf[lane] = __ldg(xtab + (int64_t)tA * MT_SLOTS + lane);
       float2 xs[2];
 #pragma unroll
       for (int ff = 0; ff < 2; ++ff) {
@@ -285,9 +253,31 @@ dsd_mask_tc_kernel(const DsdMaskArgs a, int groups_per_cta, int num_groups) {
   }
 }
 
+// (up, down, up/4, 0) of every (frame, patch slot): the sequential cross-fade of overlapadd_multi
+// (separate_dsd.py:139-169) as a per-slot recurrence; frames >= T (padding to whole groups) and slots
+// without a patch get (0, 1): they leave the accumulated masks untouched.
+__global__ void dsd_xfade_table_kernel(float4* __restrict__ tab, int T, int Tpad, int P, int tc, int overlap) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Tpad * MT_SLOTS) return;
+  const int t = i / MT_SLOTS, j = i - t * MT_SLOTS;
+  const int step = tc - overlap;
+  const float inv_ov1 = overlap > 1 ? 1.0f / (float)(overlap - 1) : 0.f;
+  int k_lo = t - tc + 1;
+  k_lo = k_lo > 0 ? (k_lo + step - 1) / step : 0;
+  int k_hi = t / step;
+  if (k_hi > P - 1) k_hi = P - 1;
+  float up = 0.f, down = 1.f;
+  if (t < T && k_lo + j <= k_hi) {
+    const int p = t - (k_lo + j) * step;
+    up = j == 0 ? 1.f : (float)p * inv_ov1;
+    down = j == 0 ? 0.f : (float)(overlap - 1 - p) * inv_ov1;
+  }
+  tab[i] = make_float4(up, down, 0.25f * up, 0.f);
+}
+
 bool dsd_mask_tc_supported(const DsdMaskArgs& a) {
   const int step = a.tc - a.overlap;
-  return step > 0 && (a.tc + step - 1) / step <= MT_SLOTS && a.ldg % 4 == 0 && a.ldg >= 52 && ((uintptr_t)a.G % 16 == 0);
+  return step > 0 && (a.tc + step - 1) / step <= MT_SLOTS && a.ldg % 4 == 0 && a.ldg >= 52 && a.ldg <= 64 && ((uintptr_t)a.G % 16 == 0);
 }
 
 // all F bins; the last 128-bin tile holds only the Nyquist bin (F = 2^k + 1)
@@ -306,7 +296,16 @@ int launch_dsd_mask_tc(dcs_ctx* ctx, const DsdMaskArgs& a, cudaStream_t st) {
   if (chunks > num_groups) chunks = num_groups;
   const int gpc = (num_groups + chunks - 1) / chunks;
   dim3 grid((unsigned)m_tiles, (unsigned)((num_groups + gpc - 1) / gpc));
-  dsd_mask_tc_kernel<<<grid, MT_THREADS, MT_SMEM, st>>>(a, gpc, num_groups);
+  // G is frame-major here: [T * 6 slots * 3 decoders][ldg] (see GemmDesc fm_*)
+  alignas(64) CUtensorMap tmG;
+  DCS_TRY(tma_encode_2d_f32(&tmG, a.G, (uint64_t)a.ldg, (uint64_t)a.T * MT_SLOTS * 3, (uint64_t)a.ldg * 4, MT_COLS));
+  const int Tpad = num_groups * MT_FRAMES;
+  DCS_TRY(ctx->net[11].ensure((size_t)Tpad * MT_SLOTS * sizeof(float4), st));
+  float4* xtab = ctx->net[11].as<float4>();
+  dsd_xfade_table_kernel<<<(unsigned)ceil_div64((int64_t)Tpad * MT_SLOTS, 256), 256, 0, st>>>(xtab, a.T, Tpad, a.P, a.tc, a.overlap);
+  DCS_CHECK_LAUNCH();
+  ctx->launches++;
+  dsd_mask_tc_kernel<<<grid, MT_THREADS, MT_SMEM, st>>>(a, tmG, xtab, gpc, num_groups);
   DCS_CHECK_LAUNCH();
   ctx->launches++;
   return DCS_OK;

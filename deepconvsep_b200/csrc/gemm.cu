@@ -84,7 +84,8 @@ gemm_f32_kernel(const GemmDesc d) {
   for (int i = 0; i < TM; ++i) {
     const int m = m0 + ty * TM + i;
     if (m >= d.M) continue;
-    const int64_t roff = (int64_t)(m / d.cm_inner) * d.c_so + (int64_t)((m % d.cm_inner) / d.cm_inner2) * d.c_si + (int64_t)(m % d.cm_inner2) * d.c_s2;
+    const int64_t roff = gemm_c_row_offset(d, m);
+    if (roff < 0) continue;
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
       const int n = n0 + tx * TN + j;
@@ -92,7 +93,7 @@ gemm_f32_kernel(const GemmDesc d) {
       float v = acc[i][j];
       if (d.bias) v += __ldg(d.bias + n);
       if (d.relu) v = fmaxf(v, 0.f);
-      d.C[roff + d.c_col0 + (int64_t)(n / d.n_seg) * d.n_ss + (n % d.n_seg)] = v;
+      d.C[roff + (int64_t)(n / d.n_seg) * d.n_ss + (n % d.n_seg)] = v;
     }
   }
 }
@@ -110,6 +111,7 @@ GemmDesc gemm_plain(const float* A, int64_t lda, const float* B, int64_t ldb, co
   d.n_seg = N > 0 ? N : 1; d.n_ss = 0; d.c_col0 = 0;
   d.relu = relu;
   d.kc_rows = 0; d.kc_unit = d.kc_pad = d.kc_n = d.kc_taps = 0;
+  d.fm_step = d.fm_tc = d.fm_T = d.fm_slots = d.fm_ndec = 0;
   return d;
 }
 

@@ -191,8 +191,8 @@ gemm_tc_kernel(const GemmDesc d, const float* __restrict__ Bhi, const float* __r
     // ------------------------------------------------------------------ epilogue
     mbar_wait_relaxed(tmem_full, 0);
     fence_after_sync();
-    const bool m_ok = m < d.M;
-    const int64_t roff = (int64_t)(mc / d.cm_inner) * d.c_so + (int64_t)((mc % d.cm_inner) / d.cm_inner2) * d.c_si + (int64_t)(mc % d.cm_inner2) * d.c_s2 + d.c_col0;
+    const int64_t roff = gemm_c_row_offset(d, mc);
+    const bool m_ok = m < d.M && roff >= 0;
     const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
     for (int j = 0; j < BN / 16; ++j) {
@@ -274,9 +274,8 @@ __global__ void splitk_reduce_kernel(const GemmDesc d, const float* __restrict__
   for (int z = 0; z < k_splits; ++z) x += partial[((int64_t)z * d.M + m) * ldp + n];   // fixed order: deterministic
   if (d.bias) x += __ldg(d.bias + n);
   if (d.relu) x = fmaxf(x, 0.f);
-  const int64_t roff = (int64_t)(m / d.cm_inner) * d.c_so + (int64_t)((m % d.cm_inner) / d.cm_inner2) * d.c_si +
-                       (int64_t)(m % d.cm_inner2) * d.c_s2 + d.c_col0;
-  d.C[roff + (int64_t)(n / d.n_seg) * d.n_ss + (n % d.n_seg)] = x;
+  const int64_t roff = gemm_c_row_offset(d, m);
+  if (roff >= 0) d.C[roff + (int64_t)(n / d.n_seg) * d.n_ss + (n % d.n_seg)] = x;
 }
 
 int launch_splitk_reduce(dcs_ctx* ctx, const GemmDesc& d, const float* partial, int ldp, int k_splits, cudaStream_t st) {

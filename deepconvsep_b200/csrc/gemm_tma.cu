@@ -211,8 +211,8 @@ gemm_tma_kernel(const GemmDesc d, const __grid_constant__ CUtensorMap tmA, const
     const int m = m_ok ? (int)m64 : 0;
     mbar_wait_relaxed(tmem_full, 0);
     fence_after_sync();
-    const int64_t roff = (int64_t)(m / d.cm_inner) * d.c_so + (int64_t)((m % d.cm_inner) / d.cm_inner2) * d.c_si +
-                         (int64_t)(m % d.cm_inner2) * d.c_s2 + d.c_col0;
+    const int64_t roff = gemm_c_row_offset(d, m);
+    const bool st_ok = m_ok && roff >= 0;
     const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
 #pragma unroll 1
     for (int j = 0; j < BN / 16; ++j) {
@@ -231,12 +231,12 @@ gemm_tma_kernel(const GemmDesc d, const __grid_constant__ CUtensorMap tmA, const
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] += w[i];
       }
-      if (m_ok && g.k_splits > 1) {   // raw partial sums; splitk_reduce adds bias / activation
+      if (st_ok && g.k_splits > 1) {   // raw partial sums; splitk_reduce adds bias / activation
         float4* dst = reinterpret_cast<float4*>(g.partial + ((int64_t)blockIdx.z * d.M + m) * g.ldp + n0 + 16 * j);
 #pragma unroll
         for (int i4 = 0; i4 < 4; ++i4)
           if (n0 + 16 * j + 4 * i4 < g.ldp) dst[i4] = make_float4(v[4 * i4], v[4 * i4 + 1], v[4 * i4 + 2], v[4 * i4 + 3]);
-      } else if (m_ok) {
+      } else if (st_ok) {
 #pragma unroll
         for (int i4 = 0; i4 < 4; ++i4) {
           const int n = n0 + 16 * j + 4 * i4;
@@ -303,6 +303,11 @@ static int encode_map(CUtensorMap* map, const float* base, int rank, const uint6
   DCS_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu pitch %llu box %u", (int)r, rank,
               (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)strides_bytes[0], box_rows);
   return DCS_OK;
+}
+
+int tma_encode_2d_f32(CUtensorMap* map, const float* base, uint64_t cols, uint64_t rows, uint64_t pitch_bytes, uint32_t box_rows) {
+  const uint64_t dims[2] = {cols, rows}, strides[1] = {pitch_bytes};
+  return encode_map(map, base, 2, dims, strides, box_rows, false);
 }
 
 // Overlapping rows (pitch < K: a convolution over time read in place) make a tensor whose row
