@@ -43,6 +43,7 @@ stft_reg_kernel(const float* __restrict__ audio, int64_t L, int hop, const float
   for (int i = tid; i < N2; i += REG_THREADS) swin[i] = __ldg(reinterpret_cast<const float2*>(win) + i);
   __syncthreads();
   const int64_t g = (int64_t)blockIdx.x * GPC + gl;
+  const bool audio_aligned8 = (reinterpret_cast<uintptr_t>(audio) & 7) == 0;
   const int64_t warp_first = ((int64_t)blockIdx.x * GPC + (tid / 32) * (32 / T)) * frames_per_group;
   for (int i = 0; i < frames_per_group; ++i) {
     if (warp_first + i >= nframes) break;  // warp-uniform: even the warp's first group is past the end
@@ -50,14 +51,26 @@ stft_reg_kernel(const float* __restrict__ audio, int64_t L, int hop, const float
     const bool valid = n < nframes;
     const int64_t base = n * hop - N / 2;
     float2 v[32];
+    // frames that lie inside the clip (all but N/hop at either end) take 8-byte loads with no bounds
+    // arithmetic: base is even, so the pairs are aligned whenever the buffer is
+    if (valid && base >= 0 && base + N <= L && audio_aligned8) {
+      const float2* __restrict__ ap = reinterpret_cast<const float2*>(audio + base);
 #pragma unroll
-    for (int a = 0; a < 32; ++a) {
-      const int idx = a * T + b;
-      const int64_t s = base + 2 * idx;
-      const float2 w = swin[idx];
-      const float x0 = (valid && s >= 0 && s < L) ? __ldg(audio + s) : 0.f;
-      const float x1 = (valid && s + 1 >= 0 && s + 1 < L) ? __ldg(audio + s + 1) : 0.f;
-      v[a] = make_float2(x0 * w.x, x1 * w.y);
+      for (int a = 0; a < 32; ++a) {
+        const int idx = a * T + b;
+        const float2 w = swin[idx], x = __ldg(ap + idx);
+        v[a] = make_float2(x.x * w.x, x.y * w.y);
+      }
+    } else {
+#pragma unroll
+      for (int a = 0; a < 32; ++a) {
+        const int idx = a * T + b;
+        const int64_t s = base + 2 * idx;
+        const float2 w = swin[idx];
+        const float x0 = (valid && s >= 0 && s < L) ? __ldg(audio + s) : 0.f;
+        const float x1 = (valid && s + 1 >= 0 && s + 1 < L) ? __ldg(audio + s + 1) : 0.f;
+        v[a] = make_float2(x0 * w.x, x1 * w.y);
+      }
     }
     G::template forward<true>(v, scr, stw, b);
 #pragma unroll
