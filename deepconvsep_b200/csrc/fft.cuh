@@ -89,6 +89,16 @@ __device__ __forceinline__ float2 real_post(const float2* Z, const float2* __res
   return cadd(e, cmul(__ldg(tw + k), o));
 }
 
+// same with the twiddle table in shared memory
+template <int N2>
+__device__ __forceinline__ float2 real_post_shared(const float2* Z, const float2* tw, int k) {
+  const float2 zk = Z[k];
+  const float2 zn = Z[(N2 - k) & (N2 - 1)];
+  const float2 e = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+  const float2 o = make_float2(0.5f * (zk.y + zn.y), -0.5f * (zk.x - zn.x));
+  return cadd(e, cmul(tw[k], o));
+}
+
 // merge step of the inverse real FFT: packed spectrum bin k (0 <= k < N2) from the half
 // spectrum S (bins 0..N2); returns conj(Z[k]) so that a FORWARD transform followed by a
 // conjugation gives the inverse.  xk = S[k], xn = S[N2-k], imaginary parts of bins 0 and N2

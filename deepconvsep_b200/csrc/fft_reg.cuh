@@ -75,12 +75,14 @@ struct FftGroup {
   // in : v[a] = x[a*T + b]                          (b = lane within the group)
   // out: v[q*T + kb] = X[(b + T*q) + 32*kb]          (q < Q, kb < T)
   // tw[j] = exp(-2*pi*i*j/(2*N2)); `scr` = this group's scratch; all lanes of the warp call this.
+  // TW_SHARED: `tw` points to a shared-memory copy of the table (plain loads) instead of global memory
+  template <bool TW_SHARED = false>
   __device__ static __forceinline__ void forward(float2 (&v)[32], float2* scr, const float2* __restrict__ tw, int b) {
     fft_dif<32>(v);
 #pragma unroll
     for (int ka = 0; ka < 32; ++ka) {
       float2 y = v[brev(ka, 5)];
-      if (ka > 0) y = cmul(y, __ldg(tw + 2 * b * ka));
+      if (ka > 0) y = cmul(y, TW_SHARED ? tw[2 * b * ka] : __ldg(tw + 2 * b * ka));
       scr[ka * PITCH + b] = y;
     }
     __syncwarp();

@@ -19,6 +19,12 @@
 namespace dcs {
 
 constexpr int REG_THREADS = 128;
+// K4 runs ONE CTA of 12 warps per SM (same 12 resident warps as three 4-warp CTAs) so that the
+// twiddle table and the synthesis window -- per-thread constants re-read for every frame -- fit in
+// shared memory next to the 12 scratch + row buffers: with ~200 KB of shared memory carved out, the
+// L1 is down to ~28 KB and those 24 KB of tables kept missing to L2 (long-scoreboard stalls were 44 %
+// of the kernel's stall samples, profiles/r1_notes.md).
+constexpr int ISTFT_THREADS = 384;
 
 template <int T>
 __global__ void __launch_bounds__(REG_THREADS)
@@ -30,7 +36,14 @@ stft_reg_kernel(const float* __restrict__ audio, int64_t L, int hop, const float
   extern __shared__ __align__(16) float2 scratch[];
   const int tid = threadIdx.x, b = tid % T, gl = tid / T;
   float2* scr = scratch + gl * G::SCRATCH;
+  // shared copies of the twiddle table and of the analysis window (per-thread constants of every frame)
+  float2* stw = scratch + GPC * G::SCRATCH;
+  float2* swin = stw + N;
+  for (int i = tid; i < N; i += REG_THREADS) stw[i] = __ldg(tw + i);
+  for (int i = tid; i < N2; i += REG_THREADS) swin[i] = __ldg(reinterpret_cast<const float2*>(win) + i);
+  __syncthreads();
   const int64_t g = (int64_t)blockIdx.x * GPC + gl;
+  const bool audio_aligned8 = (reinterpret_cast<uintptr_t>(audio) & 7) == 0;
   const int64_t warp_first = ((int64_t)blockIdx.x * GPC + (tid / 32) * (32 / T)) * frames_per_group;
   for (int i = 0; i < frames_per_group; ++i) {
     if (warp_first + i >= nframes) break;  // warp-uniform: even the warp's first group is past the end
@@ -38,16 +51,28 @@ stft_reg_kernel(const float* __restrict__ audio, int64_t L, int hop, const float
     const bool valid = n < nframes;
     const int64_t base = n * hop - N / 2;
     float2 v[32];
+    // frames that lie inside the clip (all but N/hop at either end) take 8-byte loads with no bounds
+    // arithmetic: base is even, so the pairs are aligned whenever the buffer is
+    if (valid && base >= 0 && base + N <= L && audio_aligned8) {
+      const float2* __restrict__ ap = reinterpret_cast<const float2*>(audio + base);
 #pragma unroll
-    for (int a = 0; a < 32; ++a) {
-      const int idx = a * T + b;
-      const int64_t s = base + 2 * idx;
-      const float2 w = __ldg(reinterpret_cast<const float2*>(win) + idx);
-      const float x0 = (valid && s >= 0 && s < L) ? __ldg(audio + s) : 0.f;
-      const float x1 = (valid && s + 1 >= 0 && s + 1 < L) ? __ldg(audio + s + 1) : 0.f;
-      v[a] = make_float2(x0 * w.x, x1 * w.y);
+      for (int a = 0; a < 32; ++a) {
+        const int idx = a * T + b;
+        const float2 w = swin[idx], x = __ldg(ap + idx);
+        v[a] = make_float2(x.x * w.x, x.y * w.y);
+      }
+    } else {
+#pragma unroll
+      for (int a = 0; a < 32; ++a) {
+        const int idx = a * T + b;
+        const int64_t s = base + 2 * idx;
+        const float2 w = swin[idx];
+        const float x0 = (valid && s >= 0 && s < L) ? __ldg(audio + s) : 0.f;
+        const float x1 = (valid && s + 1 >= 0 && s + 1 < L) ? __ldg(audio + s + 1) : 0.f;
+        v[a] = make_float2(x0 * w.x, x1 * w.y);
+      }
     }
-    G::forward(v, scr, tw, b);
+    G::template forward<true>(v, scr, stw, b);
 #pragma unroll
     for (int q = 0; q < G::Q; ++q)
 #pragma unroll
@@ -58,7 +83,7 @@ stft_reg_kernel(const float* __restrict__ audio, int64_t L, int hop, const float
 #pragma unroll 4
       for (int m = 0; m < N2 / T; ++m) {
         const int k = b + T * m;
-        const float2 xk = real_post<N2>(scr, tw, k);
+        const float2 xk = real_post_shared<N2>(scr, stw, k);
         if (X) X[row + k] = xk;
         if (mag) mag[row + k] = mag_scale * sqrtf(xk.x * xk.x + xk.y * xk.y);
         if (phase) phase[row + k] = atan2f(xk.y, xk.x);
@@ -81,13 +106,13 @@ stft_reg_kernel(const float* __restrict__ audio, int64_t L, int hop, const float
 }
 
 template <int T, int HS>  // HS = hop / 64: window slots (32 float2 each) per hop
-__global__ void __launch_bounds__(REG_THREADS, 3)
+__global__ void __launch_bounds__(ISTFT_THREADS, 1)
 istft_reg_kernel(const float2* __restrict__ S, int64_t nframes, int64_t ldf, int64_t src_stride,
                  const float* __restrict__ wsyn, const float* __restrict__ w2, const float2* __restrict__ tw,
                  float* __restrict__ out, int64_t Lout, int64_t out_stride, int hops_per_group, int64_t num_hops,
                  int64_t groups_per_src, int64_t total_groups) {
   using G = FftGroup<T>;
-  constexpr int N2 = G::N2, N = 2 * N2, hop = 64 * HS, R = N / hop, C0 = (N / 2) / hop, GPC = REG_THREADS / T;
+  constexpr int N2 = G::N2, N = 2 * N2, hop = 64 * HS, R = N / hop, C0 = (N / 2) / hop, GPC = ISTFT_THREADS / T;
   extern __shared__ __align__(16) float2 scratch[];
   const int tid = threadIdx.x, b = tid % T, gl = tid / T;
   float2* scr = scratch + gl * G::SCRATCH;
@@ -123,6 +148,12 @@ istft_reg_kernel(const float2* __restrict__ S, int64_t nframes, int64_t ldf, int
   constexpr int ROWP = (N2 + 1 + 7) / 8 * 8;          // float2 per staged row
   constexpr int CHUNKS = (N2 + 2) / 2;                // 16-byte pieces covering bins 0..N2
   float2* srow = scratch + GPC * G::SCRATCH + gl * ROWP;
+  // shared copies of the twiddle table (N entries, exp(-2 pi i j / N)) and of the synthesis window (as pairs)
+  float2* stw = scratch + GPC * (G::SCRATCH + ROWP);
+  float2* swsyn = stw + N;
+  for (int i = tid; i < N; i += ISTFT_THREADS) stw[i] = __ldg(tw + i);
+  for (int i = tid; i < N2; i += ISTFT_THREADS) swsyn[i] = __ldg(reinterpret_cast<const float2*>(wsyn) + i);
+  __syncthreads();
   auto prefetch = [&](int64_t nn) {
     if (nn >= 0 && nn < nframes) {
       const float2* rowp = S + (int64_t)src * src_stride + nn * ldf;
@@ -149,18 +180,18 @@ istft_reg_kernel(const float2* __restrict__ S, int64_t nframes, int64_t ldf, int
         xn = srow[N2 - idx];
       }
       if (idx == 0) { xk.y = 0.f; xn.y = 0.f; }  // irfft ignores Im of DC and Nyquist
-      v[a] = real_pre_conj(xk, xn, __ldg(tw + idx));
+      v[a] = real_pre_conj(xk, xn, stw[idx]);
     }
     __syncwarp();                    // every lane has consumed the row
     if (n < n_last) prefetch(n + 1);
-    G::forward(v, scr, tw, b);
+    G::template forward<true>(v, scr, stw, b);
     // z = conj(V)/N2: samples 2n', 2n'+1 of the frame, n' = (b + T q) + 32 kb  <->  v[q*T + kb]
 #pragma unroll
     for (int q = 0; q < G::Q; ++q)
 #pragma unroll
       for (int kb = 0; kb < T; ++kb) {
         const int np = (b + T * q) + 32 * kb;
-        const float2 w = __ldg(reinterpret_cast<const float2*>(wsyn) + np);
+        const float2 w = swsyn[np];
         const float2 r = v[q * T + kb];
         acc[q * T + kb].x = fmaf(w.x, r.x * inv_n2, acc[q * T + kb].x);
         acc[q * T + kb].y = fmaf(w.y, -r.y * inv_n2, acc[q * T + kb].y);
@@ -217,14 +248,26 @@ int launch_stft_reg(dcs_stft* p, const float* d_audio, int64_t L, float2* d_X, f
   if (p->N == 2048) {
     using G = FftGroup<32>;
     const int gpc = REG_THREADS / 32;
+    const size_t smem = (gpc * G::SCRATCH + 3 * G::N2) * sizeof(float2);   // scratch + twiddles + window
+    static bool attr = false;
+    if (!attr) {
+      DCS_CUDA(cudaFuncSetAttribute(stft_reg_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr = true;
+    }
     const unsigned grid = (unsigned)ceil_div64(nframes, (int64_t)gpc * fpg);
-    stft_reg_kernel<32><<<grid, REG_THREADS, gpc * G::SCRATCH * sizeof(float2), st>>>(
+    stft_reg_kernel<32><<<grid, REG_THREADS, smem, st>>>(
         d_audio, L, p->hop, p->d_win, p->d_tw, d_X, d_mag, d_phase, ldf, nframes, ms, fpg);
   } else {
     using G = FftGroup<16>;
     const int gpc = REG_THREADS / 16;
+    const size_t smem = (gpc * G::SCRATCH + 3 * G::N2) * sizeof(float2);
+    static bool attr = false;
+    if (!attr) {
+      DCS_CUDA(cudaFuncSetAttribute(stft_reg_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr = true;
+    }
     const unsigned grid = (unsigned)ceil_div64(nframes, (int64_t)gpc * fpg);
-    stft_reg_kernel<16><<<grid, REG_THREADS, gpc * G::SCRATCH * sizeof(float2), st>>>(
+    stft_reg_kernel<16><<<grid, REG_THREADS, smem, st>>>(
         d_audio, L, p->hop, p->d_win, p->d_tw, d_X, d_mag, d_phase, ldf, nframes, ms, fpg);
   }
   DCS_CHECK_LAUNCH();
@@ -242,7 +285,7 @@ template <int T, int HS>
 static int launch_istft_reg_t(dcs_stft* p, const float2* d_S, int nsrc, int64_t nframes, int64_t ldf, int64_t src_stride,
                               float* d_out, int64_t Lout, int64_t out_stride, cudaStream_t st) {
   using G = FftGroup<T>;
-  constexpr int GPC = REG_THREADS / T;
+  constexpr int GPC = ISTFT_THREADS / T;
   const int hop = 64 * HS;
   const int64_t num_hops = ceil_div64(Lout, hop);
   // hops per group: as long as possible (each group recomputes N/hop-1 halo frames) while every SM
@@ -257,13 +300,13 @@ static int launch_istft_reg_t(dcs_stft* p, const float2* d_S, int nsrc, int64_t 
   const int64_t total = groups_per_src * nsrc;
   const unsigned grid = (unsigned)ceil_div64(total, GPC);
   constexpr int ROWP = (G::N2 + 1 + 7) / 8 * 8;
-  const size_t smem = (size_t)GPC * (G::SCRATCH + ROWP) * sizeof(float2);
+  const size_t smem = ((size_t)GPC * (G::SCRATCH + ROWP) + 2 * G::N2 + G::N2) * sizeof(float2);   // + twiddles + window
   static bool attr = false;
   if (!attr) {
     DCS_CUDA(cudaFuncSetAttribute(istft_reg_kernel<T, HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
-  istft_reg_kernel<T, HS><<<grid, REG_THREADS, smem, st>>>(
+  istft_reg_kernel<T, HS><<<grid, ISTFT_THREADS, smem, st>>>(
       d_S, nframes, ldf, src_stride, p->d_wsyn, p->d_w2, p->d_tw, d_out, Lout, out_stride, (int)hpg, num_hops,
       groups_per_src, total);
   DCS_CHECK_LAUNCH();
