@@ -7,7 +7,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libdcs.so")
 
-ARCH_IDS = {"dsd": 0, "ikala": 1, "ikala_nopool": 2, "bach10": 3, "bach10_score": 4}
+ARCH_IDS = {"dsd": 0, "ikala": 1, "ikala_nopool": 2, "bach10": 3, "bach10_score": 4, "dsd_ild": 5}
 PATCHER_IDS = {"standalone": 0, "util": 1}
 
 
@@ -41,6 +41,7 @@ _SIGS = {
     "dcs_separate_spec": (C.c_int, [_p, _p, _p, _p, _i64, _i64, C.c_int, C.c_int, _p, _i64, _p]),
     "dcs_separate_spec_channels": (C.c_int, [_p, _p, _p, _i64, _p, _i64, _i64, C.c_int, C.c_int, _p, _i64, _p]),
     "dcs_separate_audio_score": (C.c_int, [_p, _p, _p, _p, _i64, _p, C.c_float, C.c_int, C.c_int, _p, _i64, _p]),
+    "dcs_separate_audio_stereo": (C.c_int, [_p, _p, _p, _p, _i64, _i64, C.c_float, C.c_int, C.c_int, _p, _i64, _p]),
     "dcs_xcorr_lags": (C.c_int, [_p, _p, _p, C.c_int, _i64, C.c_int, _p, _p]),
     "dcs_gemm_f32": (C.c_int, [_p, C.c_int, _p, _i64, _p, _i64, _p, _p, _i64, C.c_int, C.c_int, C.c_int, C.c_int, _p]),
     "dcs_separate_audio": (C.c_int, [_p, _p, _p, _p, _i64, C.c_float, C.c_int, C.c_int, _p, _i64, _p]),

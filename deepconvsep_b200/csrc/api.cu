@@ -242,17 +242,22 @@ static bool shape_is(const int64_t* s, int nd, int want_nd, int64_t a, int64_t b
 
 static int model_create_dsd(dcs_model* m, int nparams, const float* const* hp, const int64_t* shp, const int* nd) {
   const int F = m->F, tc = m->tc;
-  const int C1 = 50, C2 = 50, nfc = 128, kh2 = tc / 2, h2 = tc - kh2 + 1, flat = C2 * h2, ndec = 3;
-  m->C1 = C1; m->C2 = C2; m->kh2 = kh2; m->h2 = h2; m->nfc = nfc; m->ndec = ndec; m->nsrc = 4;
-  if (nparams != 15) { set_error("DSD model needs 15 parameter arrays, got %d (SURVEY.md App. A.4)", nparams); return DCS_EMODEL; }
-  const bool ok = shape_is(shp + 0, nd[0], 4, C1, 1, 1, F) && shape_is(shp + 4, nd[1], 1, C1) &&
-                  shape_is(shp + 8, nd[2], 1, C1) && shape_is(shp + 12, nd[3], 4, C2, C1, kh2, 1) &&
-                  shape_is(shp + 16, nd[4], 1, C2) && shape_is(shp + 20, nd[5], 1, C2) &&
-                  shape_is(shp + 24, nd[6], 2, flat, nfc) && shape_is(shp + 28, nd[7], 1, nfc) &&
-                  shape_is(shp + 32, nd[8], 2, nfc, flat) && shape_is(shp + 36, nd[9], 1, flat) &&
-                  shape_is(shp + 40, nd[10], 2, nfc, flat) && shape_is(shp + 44, nd[11], 1, flat) &&
-                  shape_is(shp + 48, nd[12], 2, nfc, flat) && shape_is(shp + 52, nd[13], 1, flat) &&
-                  shape_is(shp + 56, nd[14], 1, 4);
+  // DSD100 / hiphopss: 1 input channel, 128-wide bottleneck, 3 decoders feeding 4 outputs
+  // (separate_dsd.py:196-231); stereo / ILD: 2 input channels, 256-wide bottleneck, one decoder per
+  // source, 4 x 2 outputs ordered (source, channel) (trainCNN_ILD_DSD100.py:88-108)
+  const bool ild = m->arch == DCS_ARCH_DSD_ILD;
+  const int nch = ild ? 2 : 1, ndec = ild ? 4 : 3, nfc = ild ? 256 : 128, nout = 4 * nch;
+  const int C1 = 50, C2 = 50, kh2 = tc / 2, h2 = tc - kh2 + 1, flat = C2 * h2;
+  m->C1 = C1; m->C2 = C2; m->kh2 = kh2; m->h2 = h2; m->nfc = nfc; m->ndec = ndec; m->nsrc = 4; m->nch = nch;
+  const int want = 8 + 2 * ndec + 1;
+  if (nparams != want) { set_error("this DSD model needs %d parameter arrays, got %d (SURVEY.md App. A.4)", want, nparams); return DCS_EMODEL; }
+  bool ok = shape_is(shp + 0, nd[0], 4, C1, nch, 1, F) && shape_is(shp + 4, nd[1], 1, C1) &&
+            shape_is(shp + 8, nd[2], 1, C1) && shape_is(shp + 12, nd[3], 4, C2, C1, kh2, 1) &&
+            shape_is(shp + 16, nd[4], 1, C2) && shape_is(shp + 20, nd[5], 1, C2) &&
+            shape_is(shp + 24, nd[6], 2, flat, nfc) && shape_is(shp + 28, nd[7], 1, nfc) &&
+            shape_is(shp + 4 * (want - 1), nd[want - 1], 1, nout);
+  for (int d = 0; d < ndec; ++d)
+    ok = ok && shape_is(shp + 4 * (8 + 2 * d), nd[8 + 2 * d], 2, nfc, flat) && shape_is(shp + 4 * (9 + 2 * d), nd[9 + 2 * d], 1, flat);
   if (!ok) { set_error("DSD parameter shapes do not match feat_size=%d time_context=%d", F, tc); return DCS_EMODEL; }
   const int64_t ldf = dcs_padded_bins(2 * (F - 1));
   m->ldw = ldf;
@@ -262,15 +267,17 @@ static int model_create_dsd(dcs_model* m, int nparams, const float* const* hp, c
   // same pitch with zero rows at the two pad channels
   const int C1p = (C1 + 3) / 4 * 4, C2p = (C2 + 3) / 4 * 4, flatp = C2p * h2;
   m->C1p = C1p; m->C2p = C2p;
-  std::vector<float> W1f((size_t)ldf * C1, 0.f), W1t((size_t)C1 * ldf, 0.f), b1(C1), W2c((size_t)kh2 * C1p * C2, 0.f),
+  // W1f: conv1 as a GEMM weight, K index = ch * F + bin; W1t: its transpose per input channel for K3
+  std::vector<float> W1f((size_t)nch * ldf * C1, 0.f), W1t((size_t)nch * C1 * ldf, 0.f), b1(C1), W2c((size_t)kh2 * C1p * C2, 0.f),
       Wt2((size_t)kh2 * C2p * C1, 0.f), b2(C2), Wfcp((size_t)flatp * nfc, 0.f), Wdec((size_t)nfc * ndec * flatp, 0.f),
       bdec((size_t)ndec * flatp, 0.f);
   for (int f = 0; f < C1; ++f)
-    for (int b = 0; b < F; ++b) {
-      const float v = W1[(size_t)f * F + (F - 1 - b)];  // flip_filters
-      W1f[(size_t)b * C1 + f] = v;
-      W1t[(size_t)f * ldf + b] = v;
-    }
+    for (int ch = 0; ch < nch; ++ch)
+      for (int b = 0; b < F; ++b) {
+        const float v = W1[((size_t)f * nch + ch) * F + (F - 1 - b)];  // flip_filters
+        W1f[((size_t)ch * F + b) * C1 + f] = v;
+        W1t[((size_t)ch * C1 + f) * ldf + b] = v;
+      }
   for (int f = 0; f < C1; ++f) b1[f] = hp[1][f] + hp[2][f];
   for (int f = 0; f < C2; ++f) b2[f] = hp[4][f] + hp[5][f];
   for (int f = 0; f < C2; ++f)
@@ -293,7 +300,10 @@ static int model_create_dsd(dcs_model* m, int nparams, const float* const* hp, c
         for (int o = 0; o < nfc; ++o) Wdec[(size_t)o * ndec * flatp + col] = Wd[(size_t)o * flat + f * h2 + i];
       }
   }
-  std::vector<float> bout(hp[14], hp[14] + 4), bfc(hp[7], hp[7] + nfc);
+  // output bias per channel: bout[ch][s] = b[(s, ch)] (one K3 launch per channel)
+  std::vector<float> bout((size_t)nch * 4), bfc(hp[7], hp[7] + nfc);
+  for (int ch = 0; ch < nch; ++ch)
+    for (int sidx = 0; sidx < 4; ++sidx) bout[(size_t)ch * 4 + sidx] = hp[want - 1][sidx * nch + ch];
   struct { const std::vector<float>* h; float** d; } ups[] = {
       {&W1f, &m->W1f}, {&b1, &m->b1}, {&W2c, &m->W2c}, {&b2, &m->b2}, {&Wfcp, &m->Wfc}, {&bfc, &m->bfc},
       {&Wdec, &m->Wdec}, {&bdec, &m->bdec}, {&Wt2, &m->Wt2}, {&W1t, &m->W1t}, {&bout, &m->bout}};
@@ -301,7 +311,7 @@ static int model_create_dsd(dcs_model* m, int nparams, const float* const* hp, c
     DCS_TRY(upload(*u.h, u.d));
     m->dev.push_back(*u.d);
   }
-  DCS_TRY(tc_weight_create(W1f.data(), C1, F, C1, &m->tW1f));
+  DCS_TRY(tc_weight_create(W1f.data(), C1, nch * F, C1, &m->tW1f));
   DCS_TRY(tc_weight_create(W2c.data(), C2, kh2 * C1p, C2, &m->tW2c));
   DCS_TRY(tc_weight_create(Wfcp.data(), nfc, flatp, nfc, &m->tWfc));
   DCS_TRY(tc_weight_create(Wdec.data(), ndec * flatp, nfc, ndec * flatp, &m->tWdec));
@@ -319,7 +329,8 @@ int dcs_model_create(dcs_ctx* ctx, int arch, int feat_size, int time_context, in
   m->ctx = ctx; m->arch = arch; m->F = feat_size; m->tc = time_context;
   int r;
   switch (arch) {
-    case DCS_ARCH_DSD: r = model_create_dsd(m, nparams, h_params, shapes, ndims); break;
+    case DCS_ARCH_DSD:
+    case DCS_ARCH_DSD_ILD: r = model_create_dsd(m, nparams, h_params, shapes, ndims); break;
     case DCS_ARCH_IKALA:
     case DCS_ARCH_IKALA_NOPOOL:
     case DCS_ARCH_BACH10:
@@ -340,39 +351,41 @@ static int run_gemm(dcs_ctx* ctx, const GemmDesc& d, const TcWeight& w, cudaStre
   return ctx->debug_simt_gemm ? launch_gemm(ctx, d, st) : launch_gemm_tc(ctx, d, w, st);
 }
 
-static int dsd_forward(dcs_ctx* ctx, dcs_model* m, const float* d_mag, const float2* d_X, int64_t T, int64_t ldf,
-                       int overlap, int patcher, float2* d_S, int64_t src_stride, cudaStream_t st) {
+// d_mag / d_X: nch planes [T][ldf] (plane strides mag_plane / x_plane; nch = 1: the DSD100 net);
+// d_S: masked spectra, plane (s * nch + ch) at (s * nch + ch) * src_stride
+static int dsd_forward(dcs_ctx* ctx, dcs_model* m, const float* d_mag, int64_t mag_plane, const float2* d_X, int64_t x_plane,
+                       int64_t T, int64_t ldf, int overlap, int patcher, float2* d_S, int64_t src_stride, cudaStream_t st) {
   const int tc = m->tc, step = tc - overlap, C1 = m->C1, C2 = m->C2, kh2 = m->kh2, h2 = m->h2, nfc = m->nfc;
   const int C1p = m->C1p, C2p = m->C2p;   // channel pitch of H1 / H2 / the padded decoder activations
+  const int nch = m->nch, ndec = m->ndec;
   const int64_t P = dcs_num_patches(T, tc, overlap, patcher);
   if (P == 0) {  // clip shorter than one patch: nothing is predicted, every stem is silence
-    for (int s = 0; s < m->nsrc; ++s) DCS_CUDA(cudaMemsetAsync(d_S + s * src_stride, 0, (size_t)T * ldf * sizeof(float2), st));
+    for (int s = 0; s < m->nsrc * nch; ++s) DCS_CUDA(cudaMemsetAsync(d_S + s * src_stride, 0, (size_t)T * ldf * sizeof(float2), st));
     return DCS_OK;
   }
-  DCS_REQUIRE(P * 3 * tc < (int64_t)1 << 31, "clip too long (%lld patches)", (long long)P);
+  DCS_REQUIRE(P * ndec * tc < (int64_t)1 << 31, "clip too long (%lld patches)", (long long)P);
   const int64_t Tp = std::max<int64_t>(T, (P - 1) * step + tc);
   const int HP = h2 + 2 * (kh2 - 1), ldg = (C1 + 3) / 4 * 4;
   DevBuf &bH1 = ctx->net[0], &bH2 = ctx->net[1], &bz = ctx->net[2], &bap = ctx->net[3], &bG = ctx->net[4];
-  const uint64_t sig = ((uint64_t)(DCS_ARCH_DSD + 1) << 48) ^ ((uint64_t)m->F << 24) ^ (uint64_t)(tc * 64);
+  const uint64_t sig = ((uint64_t)(m->arch + 1) << 48) ^ ((uint64_t)m->F << 24) ^ (uint64_t)(tc * 64);
   // zero on (re)allocation or layout change; afterwards only the interior (rows and the C of the
   // Cp channels) is ever written, so the zero padding persists
   DCS_TRY(ensure_layout(ctx, 0, (size_t)Tp * C1p * 4, sig, st));
   DCS_TRY(ensure_layout(ctx, 1, (size_t)(Tp - kh2 + 1) * C2p * 4, sig, st));
   DCS_TRY(ensure_layout(ctx, 2, (size_t)P * nfc * 4, sig, st));
-  DCS_TRY(ensure_layout(ctx, 3, (size_t)P * 3 * HP * C2p * 4, sig, st));
-  // G: the transposed conv2 output.  For the tensor-core mask kernel it is stored frame-major
-  // ([T][6 slots][3 decoders][ldg], GemmDesc fm_*) so that a group of frames is one TMA box; the FFMA
-  // mask kernel reads the patch-major [P][3][tc][ldg] order.  Unwritten slots must stay zero / finite:
-  // the layout kind is part of the signature, so switching re-zeroes the buffer.
-  DsdMaskArgs a;
-  a.ldg = ldg; a.T = (int)T; a.P = (int)P; a.tc = tc; a.overlap = overlap; a.F = m->F; a.G = nullptr;
-  const bool mask_tc = !ctx->debug_simt_gemm && (tc + step - 1) / step <= 6;
-  const size_t g_rows = mask_tc ? (size_t)T * 6 * 3 : (size_t)P * 3 * tc;
+  DCS_TRY(ensure_layout(ctx, 3, (size_t)P * ndec * HP * C2p * 4, sig, st));
+  // G: the transposed conv2 output.  For the tensor-core mask kernel (the 3-decoder DSD100 net) it is
+  // stored frame-major ([T][6 slots][3 decoders][ldg], GemmDesc fm_*) so that a group of frames is one
+  // TMA box; the FFMA mask kernel reads the patch-major [P][ndec][tc][ldg] order.  Unwritten slots must
+  // stay zero / finite: the layout kind is part of the signature, so switching re-zeroes the buffer.
+  const bool mask_tc = !ctx->debug_simt_gemm && ndec == 3 && nch == 1 && (tc + step - 1) / step <= 6;
+  const size_t g_rows = mask_tc ? (size_t)T * 6 * 3 : (size_t)P * ndec * tc;
   DCS_TRY(ensure_layout(ctx, 4, g_rows * ldg * 4, sig ^ (mask_tc ? 0x5a5a : 0), st));
   float *H1 = bH1.as<float>(), *H2 = bH2.as<float>(), *z = bz.as<float>(), *ap = bap.as<float>(), *G = bG.as<float>();
 
-  // conv1 + both biases, once per frame (kernel height 1): H1[Tp][C1] = mag[T][F] * W1f
-  GemmDesc g1 = gemm_plain(d_mag, ldf, m->W1f, C1, m->b1, H1, C1p, (int)Tp, C1, m->F, 0);
+  // conv1 + both biases, once per frame (kernel height 1): H1[Tp][C1] = mag[T][nch x F] * W1f
+  GemmDesc g1 = gemm_plain(d_mag, ldf, m->W1f, C1, m->b1, H1, C1p, (int)Tp, C1, nch * m->F, 0);
+  if (nch > 1) { g1.k_seg = m->F; g1.k_ss = mag_plane; }   // one K segment per input channel plane
   g1.a_valid_rows = (int)T;  // util patcher: frames beyond T are zero input
   { ProfScope ps(ctx, "enc_conv1_gemm", st); DCS_TRY(run_gemm(ctx, g1, m->tW1f, st)); }
   // conv2 + both biases, once per frame offset: rows overlap in H1 (stride C1p, length kh2*C1p)
@@ -381,28 +394,36 @@ static int dsd_forward(dcs_ctx* ctx, dcs_model* m, const float* d_mag, const flo
   // bottleneck: patch k reads H2 rows k*step .. k*step+h2-1 (contiguous h2*C2p floats)
   GemmDesc g3 = gemm_plain(H2, (int64_t)step * C2p, m->Wfc, nfc, m->bfc, z, nfc, (int)P, nfc, h2 * C2p, 1);
   { ProfScope ps(ctx, "bottleneck_gemm", st); DCS_TRY(run_gemm(ctx, g3, m->tWfc, st)); }
-  // three decoder dense layers side by side, scattered into the zero-padded buffer
-  GemmDesc g4 = gemm_plain(z, nfc, m->Wdec, 3 * h2 * C2p, m->bdec, ap, (int64_t)3 * HP * C2p, (int)P, 3 * h2 * C2p, nfc, 1);
+  // the decoder dense layers side by side, scattered into the zero-padded buffer
+  GemmDesc g4 = gemm_plain(z, nfc, m->Wdec, ndec * h2 * C2p, m->bdec, ap, (int64_t)ndec * HP * C2p, (int)P, ndec * h2 * C2p, nfc, 1);
   g4.n_seg = h2 * C2p; g4.n_ss = (int64_t)HP * C2p; g4.c_col0 = (int64_t)(kh2 - 1) * C2p;
   { ProfScope ps(ctx, "dec_dense_gemm", st); DCS_TRY(run_gemm(ctx, g4, m->tWdec, st)); }
   // InverseLayer(conv2): full correlation on the padded activations, rows (k, d, u)
-  // Rows are ordered (u, k, d) -- u-major -- so that a 128-row tile holds one or two output positions
+  // Rows are ordered (u, k, d) -- u-major -- so that a 128-row tile holds one output position
   // u and can skip the taps that only see the zero padding (on average 8 of the 15).
-  GemmDesc g5 = gemm_plain(ap, 0, m->Wt2, C1, nullptr, G, ldg, (int)(P * 3 * tc), C1, kh2 * C2p, 0);
-  g5.m_inner = (int)(P * 3); g5.a_so = C2p; g5.a_si = (int64_t)HP * C2p;
-  g5.cm_inner = (int)(P * 3); g5.c_so = ldg; g5.c_si = (int64_t)tc * ldg;
-  g5.kc_rows = (int)(P * 3); g5.kc_unit = C2p; g5.kc_pad = kh2 - 1; g5.kc_n = h2; g5.kc_taps = kh2;
+  GemmDesc g5 = gemm_plain(ap, 0, m->Wt2, C1, nullptr, G, ldg, (int)(P * ndec * tc), C1, kh2 * C2p, 0);
+  g5.m_inner = (int)(P * ndec); g5.a_so = C2p; g5.a_si = (int64_t)HP * C2p;
+  g5.cm_inner = (int)(P * ndec); g5.c_so = ldg; g5.c_si = (int64_t)tc * ldg;
+  g5.kc_rows = (int)(P * ndec); g5.kc_unit = C2p; g5.kc_pad = kh2 - 1; g5.kc_n = h2; g5.kc_taps = kh2;
   if (mask_tc) { g5.fm_step = step; g5.fm_tc = tc; g5.fm_T = (int)T; g5.fm_slots = 6; g5.fm_ndec = 3; }
   { ProfScope ps(ctx, "dec_convT2_gemm", st); DCS_TRY(run_gemm(ctx, g5, m->tWt2, st)); }
-  // InverseLayer(conv1) + bias + ReLU + mask + cross-fade + phase
-  a.G = G; a.W1t = m->W1t; a.ldw = (int)m->ldw; a.bout = m->bout; a.X = d_X; a.S = d_S;
-  a.ldf = ldf; a.src_stride = src_stride;
+  // InverseLayer(conv1) + bias + ReLU + mask + cross-fade + phase; the stereo net: once per channel
+  // with that channel's conv1 weights, output biases and mixture STFT (trainCNN_ILD_DSD100.py:183-186)
   ProfScope ps(ctx, "dec_convT1_mask_xfade", st);
-  if (mask_tc) {
-    DCS_REQUIRE(dsd_mask_tc_supported(a), "dsd_forward: tensor-core mask kernel does not take this shape");
-    return launch_dsd_mask_tc(ctx, a, st);
+  for (int ch = 0; ch < nch; ++ch) {
+    DsdMaskArgs a;
+    a.G = G; a.ldg = ldg; a.W1t = m->W1t + (int64_t)ch * C1 * m->ldw; a.ldw = (int)m->ldw; a.bout = m->bout + 4 * ch;
+    a.X = d_X + ch * x_plane; a.S = d_S + ch * src_stride;
+    a.ldf = ldf; a.src_stride = nch * src_stride; a.T = (int)T; a.P = (int)P; a.tc = tc; a.overlap = overlap; a.F = m->F;
+    a.ndec = ndec;
+    if (mask_tc) {
+      DCS_REQUIRE(dsd_mask_tc_supported(a), "dsd_forward: tensor-core mask kernel does not take this shape");
+      DCS_TRY(launch_dsd_mask_tc(ctx, a, st));
+    } else {
+      DCS_TRY(launch_dsd_mask(ctx, a, st));   // FFMA kernel: > 6 patches per frame, the 4-decoder net, bring-up cross-check
+    }
   }
-  return launch_dsd_mask(ctx, a, st);   // FFMA kernel: > 6 patches per frame, or bring-up cross-check
+  return DCS_OK;
 }
 
 int dcs_separate_spec(dcs_ctx* ctx, dcs_model* m, const float* d_mag, const dcs_complex* d_X, int64_t T, int64_t ldf,
@@ -414,8 +435,10 @@ int dcs_separate_spec(dcs_ctx* ctx, dcs_model* m, const float* d_mag, const dcs_
   DCS_CUDA(cudaSetDevice(ctx->device));
   switch (m->arch) {
     case DCS_ARCH_DSD:
-      return dsd_forward(ctx, m, d_mag, (const float2*)d_X, T, ldf, overlap, patcher, (float2*)d_S, src_stride,
+      return dsd_forward(ctx, m, d_mag, 0, (const float2*)d_X, 0, T, ldf, overlap, patcher, (float2*)d_S, src_stride,
                          (cudaStream_t)stream);
+    case DCS_ARCH_DSD_ILD:
+      DCS_REQUIRE(false, "the stereo network takes two input channels: use dcs_separate_audio_stereo");
     case DCS_ARCH_IKALA:
     case DCS_ARCH_IKALA_NOPOOL:
     case DCS_ARCH_BACH10:
@@ -499,6 +522,33 @@ int dcs_gemm_f32(dcs_ctx* ctx, int engine, const float* d_A, int64_t lda, const 
     return DCS_ECUDA;
   }
   return r;
+}
+
+int dcs_separate_audio_stereo(dcs_ctx* ctx, dcs_model* m, dcs_stft* p, const float* d_audio, int64_t audio_stride, int64_t L,
+                              float scale_factor, int overlap, int patcher, float* d_stems, int64_t stem_stride, void* stream) {
+  DCS_REQUIRE(ctx && m && p && d_audio && d_stems, "dcs_separate_audio_stereo: NULL argument");
+  DCS_REQUIRE(m->arch == DCS_ARCH_DSD_ILD, "dcs_separate_audio_stereo: needs the stereo / ILD architecture");
+  DCS_REQUIRE(L > 0 && stem_stride >= L && audio_stride >= L && p->N / 2 + 1 == m->F, "dcs_separate_audio_stereo: bad length / frame size");
+  DCS_REQUIRE(overlap >= 0 && overlap < m->tc, "overlap %d must be in [0, time_context=%d)", overlap, m->tc);
+  DCS_REQUIRE(patcher == DCS_PATCHER_STANDALONE || patcher == DCS_PATCHER_UTIL, "unknown patcher %d", patcher);
+  cudaStream_t st = (cudaStream_t)stream;
+  DCS_CUDA(cudaSetDevice(ctx->device));
+  const int nch = m->nch;
+  const int64_t T = dcs_num_frames(L, p->hop), ldf = dcs_padded_bins(p->N), plane = T * ldf;
+  DCS_TRY(ctx->X.ensure((size_t)nch * plane * sizeof(float2), st));
+  DCS_TRY(ctx->mag.ensure((size_t)nch * plane * sizeof(float), st));
+  DCS_TRY(ctx->S.ensure((size_t)m->nsrc * nch * plane * sizeof(float2), st));
+  float2* X = ctx->X.as<float2>();
+  float* mag = ctx->mag.as<float>();
+  float2* S = ctx->S.as<float2>();
+  {
+    ProfScope ps(ctx, "stft_fwd", st);   // compute_transform: one STFT per channel (transform.py:105-119)
+    for (int ch = 0; ch < nch; ++ch)
+      DCS_TRY(launch_stft(p, d_audio + ch * audio_stride, L, X + ch * plane, mag + ch * plane, nullptr, scale_factor, ldf, st));
+  }
+  DCS_TRY(dsd_forward(ctx, m, mag, plane, X, plane, T, ldf, overlap, patcher, S, plane, st));
+  ProfScope ps(ctx, "istft_ola", st);
+  return launch_istft(p, S, nullptr, nullptr, 1.f, m->nsrc * nch, T, ldf, plane, d_stems, L, stem_stride, st);
 }
 
 int dcs_xcorr_lags(dcs_ctx* ctx, const float* const* h_a, const float* const* h_b, int npairs, int64_t num_samples, int flen,

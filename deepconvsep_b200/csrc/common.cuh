@@ -127,6 +127,7 @@ struct dcs_model {
   // DSD dims
   int C1, C2, kh2, h2, nfc, ndec;
   int C1p, C2p;   // channel pitch of the activation buffers (multiple of 4 floats)
+  int nch = 1;    // input channels (2: stereo / ILD net); W1t is [nch][C1][ldw], bout [nch][4]
   int64_t ldw;
   std::vector<float*> dev;  // owned device arrays
   float *W1f, *b1, *W2c, *b2, *Wfc, *bfc, *Wdec, *bdec, *Wt2, *W1t, *bout;
@@ -226,6 +227,8 @@ struct DsdMaskArgs {
   float2* S;           // [4][T][ldf]
   int64_t ldf, src_stride;
   int T, P, tc, overlap, F;
+  int ndec;            // 3: DSD100 (4th output = decoder 2, all-zero bins get 1/4); 4: one decoder per source,
+                       //    all-zero bins get 0 (stereo / ILD net, one launch per channel)
 };
 int launch_dsd_mask(dcs_ctx* ctx, const DsdMaskArgs& a, cudaStream_t st);
 // strided-conv1 families (iKala / Bach10): K3s arguments

@@ -25,11 +25,11 @@ constexpr int MASK_TILE = 256;
 constexpr int MASK_THREADS = MASK_TILE + 32;
 constexpr int MASK_MAXP = 6;
 
-template <int C1>
+template <int C1, int NDEC>
 __global__ void __launch_bounds__(MASK_THREADS)
 dsd_mask_kernel(const DsdMaskArgs a, int frames_per_cta) {
   constexpr int PITCH = (C1 + 3) / 4 * 4;
-  __shared__ __align__(16) float gs[MASK_MAXP][3][PITCH];
+  __shared__ __align__(16) float gs[MASK_MAXP][NDEC][PITCH];
   const int tid = threadIdx.x;
   int b = -1;
   if (tid < MASK_TILE) {
@@ -58,19 +58,19 @@ dsd_mask_kernel(const DsdMaskArgs a, int frames_per_cta) {
     for (int kc = k_lo; kc <= k_hi; kc += MASK_MAXP) {
       const int np = min(MASK_MAXP, k_hi - kc + 1);
       __syncthreads();
-      for (int idx = tid; idx < np * 3 * C1; idx += MASK_THREADS) {
-        const int j = idx / (3 * C1), rem = idx - j * 3 * C1;
+      for (int idx = tid; idx < np * NDEC * C1; idx += MASK_THREADS) {
+        const int j = idx / (NDEC * C1), rem = idx - j * NDEC * C1;
         const int d = rem / C1, c = rem - d * C1;
         const int k = kc + j, p = t - k * step;
-        gs[j][d][c] = __ldg(a.G + ((int64_t)(k * 3 + d) * a.tc + p) * a.ldg + c);
+        gs[j][d][c] = __ldg(a.G + ((int64_t)(k * NDEC + d) * a.tc + p) * a.ldg + c);
       }
       __syncthreads();
       if (bok) {
         for (int j = 0; j < np; ++j) {
           const int k = kc + j, p = t - k * step;
-          float y[3];
+          float y[NDEC];
 #pragma unroll
-          for (int d = 0; d < 3; ++d) {
+          for (int d = 0; d < NDEC; ++d) {
             float s0 = 0.f, s1 = 0.f;
             const float4* g4 = reinterpret_cast<const float4*>(&gs[j][d][0]);
 #pragma unroll
@@ -85,16 +85,19 @@ dsd_mask_kernel(const DsdMaskArgs a, int frames_per_cta) {
             for (int c = C1 / 4 * 4; c < C1; ++c) s0 = fmaf(w[c], gs[j][d][c], s0);
             y[d] = s0 + s1;
           }
-          // l_merge = [dec1, dec2, dec3, dec2] (separate_dsd.py:228 builds source 4 from l_fc12)
+          // NDEC == 3: l_merge = [dec1, dec2, dec3, dec2] (separate_dsd.py:228 builds source 4 from l_fc12)
+          // NDEC == 4: one decoder per source (trainCNN_ILD_DSD100.py:95-100)
           const float p0 = fmaxf(y[0] + bo0, 0.f), p1 = fmaxf(y[1] + bo1, 0.f);
-          const float p2 = fmaxf(y[2] + bo2, 0.f), p3 = fmaxf(y[1] + bo3, 0.f);
+          const float p2 = fmaxf(y[2] + bo2, 0.f), p3 = fmaxf(y[NDEC == 4 ? 3 : 1] + bo3, 0.f);
           const float tot = (p0 + p1) + (p2 + p3);
           float m0, m1, m2, m3;
           if (tot > 0.f) {
             const float r = 1.0f / tot;
             m0 = p0 * r; m1 = p1 * r; m2 = p2 * r; m3 = p3 * r;
-          } else {  // eps*rand cancels: every source gets 1/4 (separate_dsd.py:258-266)
+          } else if (NDEC == 3) {  // eps*rand cancels: every source gets 1/4 (separate_dsd.py:258-266)
             m0 = m1 = m2 = m3 = 0.25f;
+          } else {                 // prediction / (sum + eps*rand) with prediction == 0 (trainCNN_ILD_DSD100.py:185)
+            m0 = m1 = m2 = m3 = 0.f;
           }
           if (k == k_lo) {
             acc0 = m0; acc1 = m1; acc2 = m2; acc3 = m3;
@@ -125,7 +128,8 @@ int launch_dsd_mask(dcs_ctx* ctx, const DsdMaskArgs& a, cudaStream_t st) {
   DCS_REQUIRE(a.tc > a.overlap && a.overlap >= 0, "time_context %d must exceed overlap %d", a.tc, a.overlap);
   const int fpc = 16;
   dim3 grid((unsigned)ceil_div64(a.F - 1, MASK_TILE), (unsigned)ceil_div64(a.T, fpc));
-  dsd_mask_kernel<50><<<grid, MASK_THREADS, 0, st>>>(a, fpc);
+  if (a.ndec == 4) dsd_mask_kernel<50, 4><<<grid, MASK_THREADS, 0, st>>>(a, fpc);
+  else dsd_mask_kernel<50, 3><<<grid, MASK_THREADS, 0, st>>>(a, fpc);
   DCS_CHECK_LAUNCH();
   ctx->launches++;
   return DCS_OK;

@@ -290,6 +290,28 @@ class Separator(object):
                                                      outd.stride(0), _stream_ptr(stream)))
         return outd.cpu().numpy() if host else outd
 
+    def separate_stereo(self, audio, out=None, stream=None):
+        """Stereo / ILD network (examples/dsd100_2ch_ILD/trainCNN_ILD_DSD100.py:299-327): audio float
+        [L, 2] (numpy) or [2, L] (cuda tensor) -> `sep_audio` float32 [L, nsrc, 2] (numpy) or the device
+        planes [nsrc * 2, L] ordered (source, channel) (cuda tensor in -> cuda tensor out)."""
+        import torch
+        host = not hasattr(audio, "is_cuda")
+        if host:
+            a = np.asarray(audio, dtype=np.float32)
+            assert a.ndim == 2 and a.shape[1] == 2, a.shape
+            x = torch.as_tensor(np.ascontiguousarray(a.T), device="cuda")
+        else:
+            x = audio.contiguous()
+            assert x.dim() == 2 and x.shape[0] == 2 and x.dtype == torch.float32
+        L = x.shape[1]
+        outd = out if (out is not None and not host) else torch.empty((self.nsrc * 2, L), dtype=torch.float32, device=x.device)
+        _lib.check(self.lib.dcs_separate_audio_stereo(self.ctx.handle, self.model.handle, self.stft.handle, _ptr(x), x.stride(0), L,
+                                                      self.scale_factor, self.overlap, self.patcher, _ptr(outd), outd.stride(0),
+                                                      _stream_ptr(stream)))
+        if not host:
+            return outd
+        return np.ascontiguousarray(outd.cpu().numpy().reshape(self.nsrc, 2, L).transpose(2, 0, 1))
+
     def separate_spec(self, mag, X, stream=None):
         """scaled magnitude [T, ldf] + mixture STFT [T, ldf] -> masked spectra complex64 [nsrc, T, ldf]"""
         import torch

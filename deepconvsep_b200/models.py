@@ -17,6 +17,10 @@ FAMILY_DEFAULTS = {
                    sources=["bassoon", "clarinet", "saxphone", "violin"]),  # separate_bach10.py:236,325
     "bach10_score": dict(frameSize=4096, hopSize=512, window="blackmanharris", overlap=25,
                          sources=["bassoon", "clarinet", "saxphone", "violin"]),
+    # stereo / ILD trainer: transform and overlap come from its __main__ defaults
+    # (examples/dsd100_2ch_ILD/trainCNN_ILD_DSD100.py:118,147-148)
+    "dsd_ild": dict(frameSize=1024, hopSize=512, window="hanning", overlap=25,
+                    sources=["vocals", "bass", "drums", "other"]),
 }
 
 
@@ -54,6 +58,8 @@ def infer_arch(params, feat_size=None):
     s0, s3, s6 = params[0].shape, params[3].shape, params[6].shape
     if n == 15 and len(s0) == 4 and s0[0] == 50:
         return "dsd", int(s0[3]), 2 * int(s3[2])
+    if n == 17 and len(s0) == 4 and s0[0] == 50 and s0[1] == 2:
+        return "dsd_ild", int(s0[3]), 2 * int(s3[2])
     cands = (513, 1025, 2049, 257, 129, 65) if feat_size is None else (feat_size,)
     if n == 13 and s0[0] == 30:
         for F in cands:

@@ -24,13 +24,29 @@ TRAINER = {
     "dsd": dict(frameSize=1024, hopSize=512, window="blackmanharris", overlap=25),
     "ikala": dict(frameSize=1024, hopSize=512, window="blackmanharris", overlap=20),
     "bach10": dict(frameSize=4096, hopSize=512, window="blackmanharris", overlap=25),
+    # stereo / ILD trainer: transformFFT(frameSize=1024, hopSize=512, window=hanning), overlap 25
+    # (dsd100_2ch_ILD/trainCNN_ILD_DSD100.py:487, 438-441)
+    "dsd_ild": dict(frameSize=1024, hopSize=512, window="hanning", overlap=25),
 }
 
 
 def list_jobs(family, testdir, outdir):
     """[(input wav, [output wavs])] in the reference's directory conventions."""
     jobs = []
-    if family == "dsd":
+    if family == "dsd_ild":
+        # --db is the DSD100 root here: <db>/Mixtures/<sub>/<song>/mixture.wav -> <out>/Sources/<sub>/<song>/<source>.wav
+        # (trainCNN_ILD_DSD100.py:296-300, 329-343)
+        src = FAMILY_DEFAULTS["dsd_ild"]["sources"]
+        for sub in ("Dev", "Test"):
+            d = os.path.join(testdir, "Mixtures", sub)
+            if not os.path.isdir(d):
+                continue
+            for f in sorted(os.listdir(d)):
+                if f.startswith('.'):
+                    continue
+                jobs.append((os.path.join(d, f, "mixture.wav"),
+                             [os.path.join(outdir, "Sources", sub, f, s + ".wav") for s in src]))
+    elif family == "dsd":
         src = FAMILY_DEFAULTS["dsd"]["sources"]
         for sub in ("Dev", "Test"):
             d = os.path.join(testdir, sub)
@@ -67,6 +83,14 @@ def separate_dataset(family, testdir, outdir, model, scale_factor=0.3, time_cont
         wav, outs = jobs[idx]
         audioObj, sampleRate, bitrate = util.readAudioScipy(wav)
         assert sampleRate == 44100, "Sample rate needs to be 44100"
+        if family == "dsd_ild":                              # both channels in, stereo stems out
+            assert audioObj.ndim == 2 and audioObj.shape[1] == 2, "the stereo / ILD network needs 2-channel mixtures"
+            sep_audio = sep.separate_stereo(audioObj)        # [nsamples, nsrc, 2]
+            for i, path in enumerate(outs):
+                os.makedirs(os.path.dirname(path), exist_ok=True)
+                util.writeAudioScipy(path, sep_audio[:, i, :].astype(np.float64), sampleRate, bitrate)
+            seconds += audioObj.shape[0] / float(sampleRate)
+            continue
         if audioObj.ndim == 1:
             audio = audioObj
         elif family == "ikala":

@@ -44,7 +44,8 @@ enum {
   DCS_ARCH_IKALA = 1,        /* examples/ikala/separate_ikala.py:172-192 (max-pool) */
   DCS_ARCH_IKALA_NOPOOL = 2, /* examples/ikala/trainCNN.py:66-110 */
   DCS_ARCH_BACH10 = 3,       /* examples/bach10/separate_bach10.py:172-229 */
-  DCS_ARCH_BACH10_SCORE = 4  /* examples/bach10_scoreinformed/trainCNNrwc.py:134-193 */
+  DCS_ARCH_BACH10_SCORE = 4, /* examples/bach10_scoreinformed/trainCNNrwc.py:134-193 */
+  DCS_ARCH_DSD_ILD = 5       /* examples/dsd100_2ch_ILD/trainCNN_ILD_DSD100.py:66-113 (stereo in, nsrc x 2 out) */
 };
 
 /* patch generators */
@@ -149,6 +150,15 @@ int dcs_separate_audio_score(dcs_ctx* ctx, dcs_model* model, dcs_stft* plan, con
  * (separate_dsd.py:206-221) is this with relu=1.  Synchronises the stream before returning. */
 int dcs_gemm_f32(dcs_ctx* ctx, int engine, const float* d_A, int64_t lda, const float* h_B, int64_t ldb,
                  const float* h_bias, float* d_C, int64_t ldc, int M, int N, int K, int relu, void* stream);
+
+/* ---- stereo / ILD variant (examples/dsd100_2ch_ILD/trainCNN_ILD_DSD100.py:299-327) ------------ */
+/* d_audio float[2][audio_stride] (left, right; first num_samples valid) ->
+ * d_stems float[nsrc*2][stem_stride], plane (s*2 + j) = source s, channel j (`sep_audio[:, s, j]`).
+ * One STFT per channel, both scaled magnitudes into the network, per-channel masks normalised over
+ * the sources (:183-186), per-channel cross-fade, iSTFT with that channel's mixture phase. */
+int dcs_separate_audio_stereo(dcs_ctx* ctx, dcs_model* model, dcs_stft* plan, const float* d_audio,
+                              int64_t audio_stride, int64_t num_samples, float scale_factor, int overlap,
+                              int patcher, float* d_stems, int64_t stem_stride, void* stream);
 
 /* ---- evaluation: BSS-Eval 3.0 correlation lags ------------------------ */
 /* The O(num_samples) part of evaluation/bss_eval/bss_eval_sources.m: the inner products between

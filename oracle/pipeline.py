@@ -117,7 +117,7 @@ def separate_score(audio, filters, params, frameSize=4096, hopSize=512, window=N
 
 
 def separate_stereo(audio, params, frameSize=1024, hopSize=512, window=np.hanning, scale_factor=0.3,
-                    time_context=30, overlap=25, batch_size=32):
+                    time_context=30, overlap=25, batch_size=32, count_kinks=False):
     """Separation loop of the stereo / ILD trainer (trainCNN_ILD_DSD100.py:299-327):
     audio float64 [L, 2] -> stems float64 [L, nsrc, 2] (`sep_audio`).  One STFT per channel
     (`compute_transform`), util's zero-padded patcher on the [2, T, F] tensor, one network pass per
@@ -134,9 +134,25 @@ def separate_stereo(audio, params, frameSize=1024, hopSize=512, window=np.hannin
     batches, nchunks = patch.generate_overlapadd_util(mag, input_size=mag.shape[-1], time_context=time_context,
                                                       overlap=overlap, batch_size=batch_size)
     output = np.array([nets.predict_function_ild(params, b) for b in batches])   # [nb, nch, B, nsrc, tc, F]
+    kink_energy = np.zeros(nch)
+    if count_kinks:     # bins whose mask sits on its discontinuity (all outputs of a channel vanish), see separate()
+        nk, left = 0, nchunks
+        for b in batches:
+            nb = max(0, min(left, batch_size))
+            pre = nets.predict(params, b, "dsd_ild", return_pre=True)[:nb]
+            for j in range(nch):
+                flag = nets.near_kink(pre[:, j::nch], a["mask"], a["nsrc"])
+                nk += int(flag.sum())
+                kink_energy[j] += float((flag * b[:nb, j] ** 2).sum())
+            left -= batch_size
+        separate_stereo.last_kinks = nk
+        separate_stereo.last_kink_bound = np.zeros((a["nsrc"], nch))
     sep = np.zeros((audio.shape[0], a["nsrc"], nch))
     for j in range(nch):
         mm = patch.overlapadd_multi(np.swapaxes(output[:, j:j + 1], 1, 3), batches, nchunks, overlap=overlap)
+        if count_kinks:
+            for i in range(a["nsrc"]):
+                separate_stereo.last_kink_bound[i, j] = float(np.sqrt(kink_energy[j] / max(float((mm[i] ** 2).sum()), 1e-300)))
         for i in range(a["nsrc"]):
             audio_out = dsp.compute_inverse(mm[i, :phs[j].shape[0]] / scale_factor, phs[j], frameSize=frameSize,
                                             hopSize=hopSize, window=window)
