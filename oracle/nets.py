@@ -230,12 +230,14 @@ def soft_masks(pred, rule, nsrc, rand=None):
     return m
 
 
-def predict_function2(params, x, arch, rand=None):
+def predict_function2(params, x, arch, rand=None, pred=None):
     """The compiled Theano function of train_auto (separate_dsd.py:273): batch -> list of
-    nsrc arrays [B,1,tc,F] = mask_s * mixture."""
+    nsrc arrays [B,1,tc,F] = mask_s * mixture.  (`pred`: the rectified network output if the
+    caller already evaluated it.)"""
     a = ARCHS[arch]
     x = np.asarray(x, dtype=np.float64)
-    pred = predict(params, x, arch)
+    if pred is None:
+        pred = predict(params, x, arch)
     m = soft_masks(pred, a["mask"], a["nsrc"], rand)
     # score-informed: mixture estimate = sum of the input channels (trainCNNrwc.py:258)
     mix = x.sum(axis=1, keepdims=True) if a["nch"] > 1 else x[:, 0:1]

@@ -40,19 +40,27 @@ def separate(audio, params, arch, frameSize=1024, hopSize=512, window=np.hanning
     gen = patch.generate_overlapadd if patcher == "standalone" else patch.generate_overlapadd_util
     batches, nchunks = gen(mag, input_size=mag.shape[-1], time_context=time_context,
                            overlap=overlap, batch_size=batch_size)
-    output = [nets.predict_function2(params, b, arch) for b in batches]
+    pres = [nets.predict(params, b, arch, return_pre=True) for b in batches] if count_kinks else None
+    output = [nets.predict_function2(params, b, arch, pred=None if pres is None else nets.relu(pres[i]))
+              for i, b in enumerate(batches)]
     output = np.array(output)                            # [nb, nsrc, B, 1, tc, F]
     kink_energy = 0.0
     if count_kinks:
         nk, left = 0, nchunks
-        for b in batches:
+        step = time_context - overlap
+        kmap = np.zeros((max(len(ph), nchunks * step + time_context), mag.shape[-1]), dtype=bool)
+        for bi, b in enumerate(batches):
             nb = max(0, min(left, batch_size))
-            pre = nets.predict(params, b, arch, return_pre=True)[:nb]
-            flag = nets.near_kink(pre, a["mask"], a["nsrc"])           # [nb, tc, F]
+            flag = nets.near_kink(pres[bi][:nb], a["mask"], a["nsrc"])  # [nb, tc, F]
             nk += int(flag.sum())
             kink_energy += float((flag * b[:nb].sum(axis=1) ** 2).sum())
+            for i in np.nonzero(flag.reshape(nb, -1).any(axis=1))[0]:
+                k0 = (bi * batch_size + int(i)) * step
+                kmap[k0:k0 + time_context] |= flag[i]
             left -= batch_size
         separate.last_kinks = nk
+        # time-frequency bins some covering patch flags (the blended mask of such a bin is ill-conditioned)
+        separate.last_kink_map = kmap[:len(ph)]
     if nchunks == 0:
         mm = np.zeros((a["nsrc"], len(ph), mag.shape[-1]))
     else:
@@ -79,7 +87,7 @@ def separate(audio, params, arch, frameSize=1024, hopSize=512, window=np.hanning
 
 
 def separate_score(audio, filters, params, frameSize=4096, hopSize=512, window=None, scale_factor=0.2,
-                   time_context=30, overlap=25, batch_size=32, count_kinks=False):
+                   time_context=30, overlap=25, batch_size=32, count_kinks=False, return_spec=False):
     """Score-informed separation branch of examples/bach10_scoreinformed/trainCNNrwc.py:384-416:
     filters [4, T, F] float32 (LargeDatasetMask2.filterSpec) -> input channels filter*mag (float32
     products), util's zero-padded patcher on the 3-D tensor, network + Bach10 mask rule on the sum
@@ -95,17 +103,25 @@ def separate_score(audio, filters, params, frameSize=4096, hopSize=512, window=N
         masks[j] = np.asarray(filters[j], dtype=np.float32) * mag
     batches, nchunks = patch.generate_overlapadd_util(masks, input_size=masks.shape[-1], time_context=time_context,
                                                       overlap=overlap, batch_size=batch_size)
-    output = np.array([nets.predict_function2(params, b, arch) for b in batches])
+    pres = [nets.predict(params, b, arch, return_pre=True) for b in batches] if count_kinks else None
+    output = np.array([nets.predict_function2(params, b, arch, pred=None if pres is None else nets.relu(pres[i]))
+                       for i, b in enumerate(batches)])
     kink_energy = 0.0
     if count_kinks:
         nk, left = 0, nchunks
-        for b in batches:
+        step = time_context - overlap
+        kmap = np.zeros((max(len(ph), nchunks * step + time_context), mag.shape[-1]), dtype=bool)
+        for bi, b in enumerate(batches):
             nb = max(0, min(left, batch_size))
-            flag = nets.near_kink(nets.predict(params, b, arch, return_pre=True)[:nb], a["mask"], a["nsrc"])
+            flag = nets.near_kink(pres[bi][:nb], a["mask"], a["nsrc"])
             nk += int(flag.sum())
             kink_energy += float((flag * b[:nb].sum(axis=1) ** 2).sum())
+            for i in np.nonzero(flag.reshape(nb, -1).any(axis=1))[0]:
+                k0 = (bi * batch_size + int(i)) * step
+                kmap[k0:k0 + time_context] |= flag[i]
             left -= batch_size
         separate_score.last_kinks = nk
+        separate_score.last_kink_map = kmap[:len(ph)]
     mm = patch.overlapadd_multi(output, batches, nchunks, overlap=overlap)
     if count_kinks:
         separate_score.last_kink_bound = [float(np.sqrt(kink_energy / max(float((mm[i] ** 2).sum()), 1e-300))) for i in range(4)]
@@ -113,6 +129,8 @@ def separate_score(audio, filters, params, frameSize=4096, hopSize=512, window=N
     for i in range(4):
         audio_out = dsp.compute_inverse(mm[i, :len(ph)] / scale_factor, ph, frameSize=frameSize, hopSize=hopSize, window=window)
         stems.append(audio_out[:len(audio)] if len(audio_out) > len(audio) else audio_out)
+    if return_spec:
+        return np.stack(stems), mag, ph, mm
     return np.stack(stems)
 
 

@@ -1,0 +1,101 @@
+"""Strict parity comparison shared by the GPU tests (TEST INFRASTRUCTURE: uses oracle/).
+
+North-star tolerance: per-stem relative L2 on the float waveform <= 1e-4 against the float64 oracle,
+with NO whole-stem allowance.
+
+The reference's soft mask is discontinuous where every rectified source output vanishes
+(`oracle.nets.near_kink`): a (patch, frame, bin) whose float64 pre-activation lies within ~2e-8 of that
+jump lands on either side in ANY finite-precision evaluation, and the two sides differ by O(1) in the
+mask.  The oracle flags those time-frequency bins (a few per million).  They are taken out of the
+comparison *bin by bin* -- not by widening the tolerance of the whole stem:
+
+  1. the CUDA pipeline runs with the spectrum tap on, so the blended masked spectra it fed to its
+     inverse STFT are observable (`Separator.separate_tapped`);
+  2. at the flagged bins -- and only there -- the oracle's spectrum is replaced by the device's value
+     (the iSTFT is linear, so this is `want + istft(D)`, D non-zero at the flagged bins only), after
+     checking that the device value is admissible there (|S| <= |X|: a mask in [0, 1]);
+  3. the waveform comparison is then made at the plain 1e-4 bar for every stem.
+
+With no flagged bin (kink-free seeds) step 2 is the identity and the comparison is the unmodified one.
+Every case appends its measured errors to gpurun_out/parity_r2.jsonl (copied to profiles/ when
+committed)."""
+import json
+import os
+
+import numpy as np
+
+from oracle import dsp
+
+TOL = 1e-4
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def rel(a, b):
+    return float(np.linalg.norm(np.asarray(a, dtype=np.float64) - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def record(name, **fields):
+    d = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "parity_r2.jsonl"), "a") as f:
+            f.write(json.dumps(dict(case=name, **fields)) + "\n")
+    except OSError:
+        pass
+
+
+def istft_rows(D, rows, win, hop, N, length):
+    """dsp.istft_norm (transform.py:367-396) of a spectrogram whose only non-zero frames are `rows`
+    (exact: the transform is linear and its normaliser does not depend on the data)."""
+    T = D.shape[0]
+    total = hop * (T - 1) + N
+    data = np.zeros(total)
+    norm = np.zeros(total)
+    w2 = win * win
+    for n in range(T):
+        norm[n * hop:n * hop + N] += w2
+    for n in rows:
+        data[n * hop:n * hop + N] += win * np.fft.irfft(D[n], N)[:N]
+    data, norm = data[N // 2:], norm[N // 2:]
+    norm[norm == 0] = 1.0
+    return (data / norm)[:length]
+
+
+def strict_check(name, got, S_dev, want, mag, ph, mm, kmap, N, hop, window, scale, tol=TOL, extra=None):
+    """got float32 [nsrc, L] (device stems), S_dev complex [nsrc, T, F] (device spectra, tap),
+    want/mag/ph/mm = oracle.pipeline.separate(..., return_spec=True), kmap bool [T, F] = bins the
+    oracle flags.  Returns the per-stem errors after asserting them."""
+    nsrc, L = want.shape
+    T, F = ph.shape
+    win = window(N) if callable(window) else np.asarray(window, dtype=np.float64)
+    raw = [rel(got[s], want[s]) for s in range(nsrc)]
+    nflag = int(kmap.sum())
+    X = (np.asarray(mag, dtype=np.float64) / scale) * np.sqrt(N)       # |X| as the oracle saw it
+    S_or = (mm[:, :T] / scale) * np.sqrt(N) * np.exp(1j * ph)[None]
+    S_dev = np.asarray(S_dev)[:, :T, :F].astype(np.complex128)
+    # spectrum level, flagged bins excluded
+    keep = ~kmap
+    spec = [float(np.linalg.norm((S_dev[s] - S_or[s])[keep]) / max(np.linalg.norm(S_or[s]), 1e-30)) for s in range(nsrc)]
+    errs = raw
+    if nflag:
+        assert nflag <= 1e-4 * kmap.size + 8, ("too many ill-conditioned bins for a meaningful comparison", nflag, kmap.size)
+        tt, ff = np.nonzero(kmap)
+        # admissible at the flagged bins: each blended mask in [0, 1] (up to fp32 rounding)
+        for s in range(nsrc):
+            assert np.all(np.abs(S_dev[s][tt, ff]) <= X[tt, ff] * (1 + 1e-4) + 1e-12), (name, s)
+        rows = sorted(set(int(t) for t in tt))
+        errs = []
+        for s in range(nsrc):
+            D = np.zeros((T, F), dtype=np.complex128)
+            D[tt, ff] = S_dev[s][tt, ff] - S_or[s][tt, ff]
+            sub = want[s] + istft_rows(D, rows, win, hop, N, L)
+            errs.append(rel(got[s], sub))
+    rec = dict(N=N, hop=hop, seconds=L / 44100.0, nsrc=nsrc, flagged_bins=nflag, total_bins=int(kmap.size),
+               rel_l2=errs, rel_l2_unmodified=raw, rel_l2_spectrum_flagged_excluded=spec, tol=tol)
+    if extra:
+        rec.update(extra)
+    record(name, **rec)
+    for s in range(nsrc):
+        assert errs[s] <= tol, (name, s, errs[s], raw[s], nflag)
+        assert spec[s] <= tol, (name, "spectrum", s, spec[s])
+    return errs
