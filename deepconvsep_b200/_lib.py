@@ -24,6 +24,8 @@ _SIGS = {
     "dcs_destroy": (C.c_int, [_p]),
     "dcs_workspace_bytes": (_i64, [_p]),
     "dcs_launch_count": (_i64, [_p]),
+    "dcs_set_spectrum_tap": (C.c_int, [_p, _p, _i64]),
+    "dcs_set_pool_tap": (C.c_int, [_p, _p, _i64]),
     "dcs_profile": (C.c_int, [_p, C.c_int]),
     "dcs_profile_read": (C.c_int, [_p, C.c_char_p, C.c_int, _p, C.c_int]),
     "dcs_stft_plan": (C.c_int, [_p, C.c_int, C.c_int, _p, _p, C.POINTER(_p)]),

@@ -4,6 +4,9 @@
 #include <math.h>
 #include <string.h>
 #include <stdlib.h>
+#include <map>
+#include <mutex>
+#include <utility>
 #include <vector>
 #include "common.cuh"
 
@@ -44,6 +47,20 @@ void DevBuf::release() {
   if (p) cudaFree(p);
   p = nullptr;
   cap = 0;
+}
+
+int ensure_smem_attr_impl(const void* kernel, int bytes) {
+  int dev = 0;
+  DCS_CUDA(cudaGetDevice(&dev));
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, int> done;
+  std::lock_guard<std::mutex> g(mu);
+  const auto key = std::make_pair(kernel, dev);
+  const auto it = done.find(key);
+  if (it != done.end() && it->second >= bytes) return DCS_OK;
+  DCS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  done[key] = bytes;
+  return DCS_OK;
 }
 
 int upload(const std::vector<float>& h, float** d) {
@@ -120,6 +137,28 @@ int dcs_destroy(dcs_ctx* c) {
 int64_t dcs_workspace_bytes(const dcs_ctx* c) { return c ? c->workspace_bytes() : 0; }
 int64_t dcs_launch_count(const dcs_ctx* c) { return c ? c->launches : 0; }
 
+int dcs_set_spectrum_tap(dcs_ctx* c, dcs_complex* d_S, int64_t capacity) {
+  DCS_REQUIRE(c != nullptr && capacity >= 0, "dcs_set_spectrum_tap: bad argument");
+  c->tap = (float2*)d_S;
+  c->tap_cap = d_S ? capacity : 0;
+  return DCS_OK;
+}
+
+int dcs_set_pool_tap(dcs_ctx* c, uint8_t* d_bits, int64_t capacity) {
+  DCS_REQUIRE(c != nullptr && capacity >= 0, "dcs_set_pool_tap: bad argument");
+  c->pool_tap = d_bits;
+  c->pool_tap_cap = d_bits ? capacity : 0;
+  return DCS_OK;
+}
+
+// the blended masked spectra the inverse STFT of this call consumed -> the caller's tap buffer
+static int copy_tap(dcs_ctx* c, const float2* S, int64_t elems, cudaStream_t st) {
+  if (!c->tap) return DCS_OK;
+  DCS_REQUIRE(c->tap_cap >= elems, "spectrum tap holds %lld elements, this call produced %lld", (long long)c->tap_cap, (long long)elems);
+  DCS_CUDA(cudaMemcpyAsync(c->tap, S, (size_t)elems * sizeof(float2), cudaMemcpyDeviceToDevice, st));
+  return DCS_OK;
+}
+
 int dcs_profile(dcs_ctx* c, int enable) {
   DCS_REQUIRE(c != nullptr, "dcs_profile: NULL ctx");
   c->prof_on = enable != 0;
@@ -191,18 +230,21 @@ int dcs_stft_plan_destroy(dcs_stft* p) {
 int dcs_stft_forward(dcs_stft* p, const float* d_audio, int64_t L, dcs_complex* d_X, float* d_mag, float mag_scale,
                      int64_t ldf, void* stream) {
   DCS_REQUIRE(p && d_audio && L > 0, "dcs_stft_forward: bad argument");
+  DCS_CUDA(cudaSetDevice(p->ctx->device));
   return launch_stft(p, d_audio, L, (float2*)d_X, d_mag, nullptr, mag_scale, ldf, (cudaStream_t)stream);
 }
 
 int dcs_stft_forward_polar(dcs_stft* p, const float* d_audio, int64_t L, float* d_mag, float* d_phase, float mag_scale,
                            int64_t ldf, void* stream) {
   DCS_REQUIRE(p && d_audio && L > 0, "dcs_stft_forward_polar: bad argument");
+  DCS_CUDA(cudaSetDevice(p->ctx->device));
   return launch_stft(p, d_audio, L, nullptr, d_mag, d_phase, mag_scale, ldf, (cudaStream_t)stream);
 }
 
 int dcs_istft(dcs_stft* p, const dcs_complex* d_S, int nsrc, int64_t T, int64_t ldf, int64_t src_stride, float* d_out,
               int64_t Lout, int64_t out_stride, void* stream) {
   DCS_REQUIRE(p && d_S && d_out && T > 0, "dcs_istft: bad argument");
+  DCS_CUDA(cudaSetDevice(p->ctx->device));
   return launch_istft(p, (const float2*)d_S, nullptr, nullptr, 1.f, nsrc, T, ldf, src_stride, d_out, Lout, out_stride,
                       (cudaStream_t)stream);
 }
@@ -210,6 +252,7 @@ int dcs_istft(dcs_stft* p, const dcs_complex* d_S, int nsrc, int64_t T, int64_t 
 int dcs_istft_polar(dcs_stft* p, dcs_ctx* ctx, const float* d_mag, const float* d_phase, float mag_scale, int64_t T,
                     int64_t ldf, float* d_out, int64_t Lout, void* stream) {
   DCS_REQUIRE(p && d_mag && d_phase && d_out && T > 0, "dcs_istft_polar: bad argument");
+  DCS_CUDA(cudaSetDevice(p->ctx->device));
   (void)ctx;
   return launch_istft(p, nullptr, d_mag, d_phase, mag_scale * sqrtf((float)p->N), 1, T, ldf, 0, d_out, Lout, Lout,
                       (cudaStream_t)stream);
@@ -482,6 +525,7 @@ int dcs_separate_audio_score(dcs_ctx* ctx, dcs_model* m, dcs_stft* p, const floa
   { ProfScope ps(ctx, "stft_fwd", st); DCS_TRY(launch_stft(p, d_audio, L, X, mag, nullptr, scale_factor, ldf, st)); }
   { ProfScope ps(ctx, "score_channels", st); DCS_TRY(launch_channel_mul(ctx, mag, d_filters, chans, plane, 4, st)); }
   DCS_TRY(sconv_forward(ctx, m, chans, plane, X, T, ldf, overlap, patcher, S, plane, st));
+  DCS_TRY(copy_tap(ctx, S, (int64_t)m->nsrc * plane, st));
   ProfScope ps(ctx, "istft_ola", st);
   return launch_istft(p, S, nullptr, nullptr, 1.f, m->nsrc, T, ldf, plane, d_stems, L, stem_stride, st);
 }
@@ -547,6 +591,7 @@ int dcs_separate_audio_stereo(dcs_ctx* ctx, dcs_model* m, dcs_stft* p, const flo
       DCS_TRY(launch_stft(p, d_audio + ch * audio_stride, L, X + ch * plane, mag + ch * plane, nullptr, scale_factor, ldf, st));
   }
   DCS_TRY(dsd_forward(ctx, m, mag, plane, X, plane, T, ldf, overlap, patcher, S, plane, st));
+  DCS_TRY(copy_tap(ctx, S, (int64_t)m->nsrc * nch * plane, st));
   ProfScope ps(ctx, "istft_ola", st);
   return launch_istft(p, S, nullptr, nullptr, 1.f, m->nsrc * nch, T, ldf, plane, d_stems, L, stem_stride, st);
 }
@@ -574,6 +619,7 @@ int dcs_separate_audio(dcs_ctx* ctx, dcs_model* m, dcs_stft* p, const float* d_a
   float2* S = ctx->S.as<float2>();
   { ProfScope ps(ctx, "stft_fwd", st); DCS_TRY(launch_stft(p, d_audio, L, X, mag, nullptr, scale_factor, ldf, st)); }
   DCS_TRY(dcs_separate_spec(ctx, m, mag, (const dcs_complex*)X, T, ldf, overlap, patcher, (dcs_complex*)S, T * ldf, stream));
+  DCS_TRY(copy_tap(ctx, S, (int64_t)m->nsrc * T * ldf, st));
   ProfScope ps(ctx, "istft_ola", st);
   return launch_istft(p, S, nullptr, nullptr, 1.f, m->nsrc, T, ldf, T * ldf, d_stems, L, stem_stride, st);
 }

@@ -38,6 +38,11 @@ void set_error(const char* fmt, ...);
     if (_r != DCS_OK) return _r; \
   } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE property of a kernel: remembered per
+// (kernel, current device), thread-safe (api.cu).  Call with the ctx's device current.
+int ensure_smem_attr_impl(const void* kernel, int bytes);
+template <typename K> inline int ensure_smem_attr(K kernel, int bytes) { return ensure_smem_attr_impl((const void*)kernel, bytes); }
+
 __host__ __device__ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // grow-only device buffer; newly allocated memory is zero-filled
@@ -75,6 +80,10 @@ struct dcs_ctx {
   dcs::DevBuf audio, X, mag, S, stems, pcm_in, pcm_out;
   dcs::DevBuf net[12];
   uint64_t net_sig[12] = {0};   // layout signature of what each net[] buffer currently holds
+  float2* tap = nullptr;        // dcs_set_spectrum_tap: copy of the masked spectra the iSTFT consumed
+  int64_t tap_cap = 0;
+  uint8_t* pool_tap = nullptr;  // dcs_set_pool_tap: copy of the max-pool tie bits of the forward pass
+  int64_t pool_tap_cap = 0;
   int64_t workspace_bytes() const;
 };
 

@@ -284,11 +284,7 @@ bool dsd_mask_tc_supported(const DsdMaskArgs& a) {
 int launch_dsd_mask_tc(dcs_ctx* ctx, const DsdMaskArgs& a, cudaStream_t st) {
   if (a.T <= 0) return DCS_OK;
   DCS_REQUIRE(dsd_mask_tc_supported(a), "dsd_mask_tc: unsupported shape");
-  static bool attr = false;
-  if (!attr) {
-    DCS_CUDA(cudaFuncSetAttribute(dsd_mask_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MT_SMEM));
-    attr = true;
-  }
+  DCS_TRY(ensure_smem_attr(dsd_mask_tc_kernel, MT_SMEM));
   const int m_tiles = (a.F + MT_BINS - 1) / MT_BINS;
   const int num_groups = (a.T + MT_FRAMES - 1) / MT_FRAMES;
   int chunks = ctx->num_sms / m_tiles;

@@ -320,12 +320,8 @@ void tc_weight_destroy(TcWeight* w) {
 template <int BN, int STAGES, int AVEC>
 static int launch_tc(dcs_ctx* ctx, const GemmDesc& d, const TcWeight& w, cudaStream_t st) {
   using SM = TcSmem<BN, STAGES>;
-  static bool attr = false;
-  if (!attr) {
-    DCS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, AVEC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
-    DCS_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, AVEC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
-    attr = true;
-  }
+  DCS_TRY(ensure_smem_attr(gemm_tc_kernel<BN, STAGES, AVEC, false>, SM::TOTAL));
+  DCS_TRY(ensure_smem_attr(gemm_tc_kernel<BN, STAGES, AVEC, true>, SM::TOTAL));
   const int m_tiles = (int)ceil_div64(d.M, TC_BM), n_tiles = (int)ceil_div64(d.N, BN);
   const int num_kb = (d.K + KSTAGE - 1) / KSTAGE;
   // skinny GEMMs (few output tiles, long K -- the bottleneck dense layers): split K over otherwise idle SMs

@@ -27,6 +27,7 @@
 //    (q, w): the box {32, 128 positions, 1, 1} at (0, pos0 + w, u + q, kd) -- implicit GEMM, no
 //    im2col and no per-row address arithmetic anywhere.
 // Rows / positions / taps outside the tensor are zero-filled by the TMA unit.
+#include <atomic>
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -274,15 +275,13 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 static EncodeTiledFn encode_tiled_fn() {
   // the driver entry point is fetched through the runtime: libdcs.so links cudart statically and
   // does not link libcuda
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  static const EncodeTiledFn fn = [] {   // C++11 magic static: initialised once, thread-safe
     void* p = nullptr;
     cudaDriverEntryPointQueryResult q;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)p;
-  }
+      return (EncodeTiledFn)p;
+    return (EncodeTiledFn) nullptr;
+  }();
   return fn;
 }
 
@@ -314,7 +313,7 @@ int tma_encode_2d_f32(CUtensorMap* map, const float* base, uint64_t cols, uint64
 // pitch is smaller than its row extent.  The copy engine only does address arithmetic and a
 // per-dimension bounds check, so it works; should a driver refuse to encode such a map, the GEMM
 // stays on the register-staged kernel (remembered here).
-static bool g_overlap_rejected = false;
+static std::atomic<bool> g_overlap_rejected{false};   // a property of the driver: process-wide is right
 
 // how the copy engine can address the A view of `d`
 struct TmaView {
@@ -408,11 +407,7 @@ void tc_weight_encode_maps(TcWeight* w) {
 template <int BN, int STAGES>
 static int launch_tma(dcs_ctx* ctx, const GemmDesc& d, const TcWeight& w, cudaStream_t st) {
   using SM = TmSmem<BN, STAGES>;
-  static bool attr = false;
-  if (!attr) {
-    DCS_CUDA(cudaFuncSetAttribute(gemm_tma_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
-    attr = true;
-  }
+  DCS_TRY(ensure_smem_attr(gemm_tma_kernel<BN, STAGES>, SM::TOTAL));
   constexpr int slot = BN == 32 ? 0 : (BN == 64 ? 1 : 2);
   if (!w.tmap_ok[slot]) {   // normally done by tc_weight_encode_maps at weight creation
     const uint64_t dims[2] = {(uint64_t)w.Kp, (uint64_t)2 * w.Np}, strides[1] = {(uint64_t)w.Kp * 4};

@@ -163,12 +163,7 @@ template <int STRIDE, int ND, int NSRC, int NDEC, int RULE, int POOL, int NW>
 static int launch_sconv_t(dcs_ctx* ctx, const SconvMaskArgs& a, cudaStream_t st) {
   constexpr int JT = SC_TILE + ND - 1;
   const size_t smem = (size_t)(NDEC * JT * 33 + 4) * sizeof(float) + NW * ND * 32 * sizeof(float4);
-  static bool attr = false;
-  if (!attr) {
-    DCS_CUDA(cudaFuncSetAttribute(sconv_mask_kernel<STRIDE, ND, NSRC, NDEC, RULE, POOL, NW>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
+  DCS_TRY(ensure_smem_attr(sconv_mask_kernel<STRIDE, ND, NSRC, NDEC, RULE, POOL, NW>, (int)smem));
   const int mtot = (a.F + STRIDE - 1) / STRIDE;
   dim3 grid((unsigned)ceil_div64(mtot, SC_TILE), (unsigned)a.T);
   sconv_mask_kernel<STRIDE, ND, NSRC, NDEC, RULE, POOL, NW><<<grid, SC_TILE, smem, st>>>(a);

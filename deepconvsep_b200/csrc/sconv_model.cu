@@ -174,6 +174,11 @@ int sconv_forward(dcs_ctx* ctx, dcs_model* m, const float* d_in, int64_t in_plan
   if (c.pool) {
     ProfScope ps(ctx, "enc_maxpool", st);
     DCS_TRY(launch_pool4(ctx, H1, Hp, tie, Tp, J, WP, st));
+    if (ctx->pool_tap) {   // inspection tap (parity tests): the discrete un-pool routing decisions of this call
+      const int64_t n = T * WP * CP;
+      DCS_REQUIRE(ctx->pool_tap_cap >= n, "pool tap holds %lld bytes, this call produced %lld", (long long)ctx->pool_tap_cap, (long long)n);
+      DCS_CUDA(cudaMemcpyAsync(ctx->pool_tap, tie, (size_t)n, cudaMemcpyDeviceToDevice, st));
+    }
   }
   {  // conv2 + biases, once per (frame offset u, position v): K = kh2 time taps x (kw2 x 32) contiguous
     ProfScope ps(ctx, "enc_conv2_gemm", st);

@@ -215,11 +215,7 @@ static int launch_istft_n(dcs_stft* p, const float2* d_S, const float* d_mag, co
   const int64_t span = (int64_t)hpc * p->hop;
   const size_t dyn = (size_t)span * sizeof(float);
   dim3 grid((unsigned)ceil_div64(Lout, span), (unsigned)nsrc);
-  static bool attr_set = false;
-  if (!attr_set) {
-    DCS_CUDA(cudaFuncSetAttribute(istft_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr_set = true;
-  }
+  DCS_TRY(ensure_smem_attr(istft_kernel<N>, 96 * 1024));
   istft_kernel<N><<<grid, N / 8, dyn, st>>>(d_S, d_mag, d_phase, polar_scale, T, ldf, src_stride, p->d_wsyn, p->d_w2,
                                             p->d_tw, d_out, Lout, out_stride, p->hop, hpc);
   DCS_CHECK_LAUNCH();

@@ -249,11 +249,7 @@ int launch_stft_reg(dcs_stft* p, const float* d_audio, int64_t L, float2* d_X, f
     using G = FftGroup<32>;
     const int gpc = REG_THREADS / 32;
     const size_t smem = (gpc * G::SCRATCH + 3 * G::N2) * sizeof(float2);   // scratch + twiddles + window
-    static bool attr = false;
-    if (!attr) {
-      DCS_CUDA(cudaFuncSetAttribute(stft_reg_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr = true;
-    }
+    DCS_TRY(ensure_smem_attr(stft_reg_kernel<32>, (int)smem));
     const unsigned grid = (unsigned)ceil_div64(nframes, (int64_t)gpc * fpg);
     stft_reg_kernel<32><<<grid, REG_THREADS, smem, st>>>(
         d_audio, L, p->hop, p->d_win, p->d_tw, d_X, d_mag, d_phase, ldf, nframes, ms, fpg);
@@ -261,11 +257,7 @@ int launch_stft_reg(dcs_stft* p, const float* d_audio, int64_t L, float2* d_X, f
     using G = FftGroup<16>;
     const int gpc = REG_THREADS / 16;
     const size_t smem = (gpc * G::SCRATCH + 3 * G::N2) * sizeof(float2);
-    static bool attr = false;
-    if (!attr) {
-      DCS_CUDA(cudaFuncSetAttribute(stft_reg_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr = true;
-    }
+    DCS_TRY(ensure_smem_attr(stft_reg_kernel<16>, (int)smem));
     const unsigned grid = (unsigned)ceil_div64(nframes, (int64_t)gpc * fpg);
     stft_reg_kernel<16><<<grid, REG_THREADS, smem, st>>>(
         d_audio, L, p->hop, p->d_win, p->d_tw, d_X, d_mag, d_phase, ldf, nframes, ms, fpg);
@@ -301,11 +293,7 @@ static int launch_istft_reg_t(dcs_stft* p, const float2* d_S, int nsrc, int64_t 
   const unsigned grid = (unsigned)ceil_div64(total, GPC);
   constexpr int ROWP = (G::N2 + 1 + 7) / 8 * 8;
   const size_t smem = ((size_t)GPC * (G::SCRATCH + ROWP) + 2 * G::N2 + G::N2) * sizeof(float2);   // + twiddles + window
-  static bool attr = false;
-  if (!attr) {
-    DCS_CUDA(cudaFuncSetAttribute(istft_reg_kernel<T, HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
+  DCS_TRY(ensure_smem_attr(istft_reg_kernel<T, HS>, (int)smem));
   istft_reg_kernel<T, HS><<<grid, ISTFT_THREADS, smem, st>>>(
       d_S, nframes, ldf, src_stride, p->d_wsyn, p->d_w2, p->d_tw, d_out, Lout, out_stride, (int)hpg, num_hops,
       groups_per_src, total);

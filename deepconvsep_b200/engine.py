@@ -38,9 +38,11 @@ def _ptr(a):
     return a.data_ptr()
 
 
-def _stream_ptr(stream=None):
+def _stream_ptr(stream=None, device=None):
+    """cudaStream_t of `stream`, or of torch's current stream ON `device` (the ctx's device: the
+    current stream of another device would be a handle the library cannot launch on)."""
     import torch
-    s = stream if stream is not None else torch.cuda.current_stream()
+    s = stream if stream is not None else torch.cuda.current_stream(device)
     return C.c_void_p(s.cuda_stream)
 
 
@@ -83,7 +85,7 @@ class Context(object):
         Cd = torch.empty((M, N), dtype=torch.float32, device=A.device)
         _lib.check(self.lib.dcs_gemm_f32(self.handle, int(engine), _ptr(A), A.stride(0), Bh.ctypes.data, N,
                                          None if bh is None else bh.ctypes.data, _ptr(Cd), N, M, N, K, int(relu),
-                                         _stream_ptr(stream)))
+                                         _stream_ptr(stream, self.device)))
         return Cd
 
     def close(self):
@@ -104,6 +106,7 @@ class Stft(object):
     def __init__(self, ctx, frame_size, hop, window=np.hanning, syn_window=None):
         self.ctx, self.lib = ctx, ctx.lib
         self.N, self.hop = int(frame_size), int(hop)
+        self.device = ctx.device
         self.F = self.N // 2 + 1
         self.ldf = int(self.lib.dcs_padded_bins(self.N))
         self.window = np.ascontiguousarray(get_window(window, self.N), dtype=np.float64)
@@ -112,6 +115,11 @@ class Stft(object):
         _lib.check(self.lib.dcs_stft_plan(ctx.handle, self.N, self.hop, self.window.ctypes.data,
                                           None if syn is None else syn.ctypes.data, C.byref(h)))
         self.handle = h
+
+    @property
+    def dev(self):
+        import torch
+        return torch.device("cuda", self.device)
 
     def num_frames(self, L):
         return int(self.lib.dcs_num_frames(int(L), self.hop))
@@ -128,7 +136,7 @@ class Stft(object):
         X = torch.empty((T, self.ldf), dtype=torch.complex64, device=audio.device) if want_X else None
         mag = torch.empty((T, self.ldf), dtype=torch.float32, device=audio.device) if want_mag else None
         _lib.check(self.lib.dcs_stft_forward(self.handle, _ptr(audio), L, _ptr(X), _ptr(mag), float(mag_scale),
-                                             self.ldf, _stream_ptr(stream)))
+                                             self.ldf, _stream_ptr(stream, self.device)))
         return X, mag
 
     def forward_polar(self, audio, mag_scale=1.0, stream=None):
@@ -138,7 +146,7 @@ class Stft(object):
         mag = torch.empty((T, self.ldf), dtype=torch.float32, device=audio.device)
         ph = torch.empty((T, self.ldf), dtype=torch.float32, device=audio.device)
         _lib.check(self.lib.dcs_stft_forward_polar(self.handle, _ptr(audio), L, _ptr(mag), _ptr(ph), float(mag_scale),
-                                                   self.ldf, _stream_ptr(stream)))
+                                                   self.ldf, _stream_ptr(stream, self.device)))
         return mag, ph
 
     def inverse(self, S, num_out=None, stream=None):
@@ -150,7 +158,7 @@ class Stft(object):
         assert S.is_contiguous() and ldf >= self.F
         n = self.out_length(T) if num_out is None else int(num_out)
         out = torch.empty((nsrc, n), dtype=torch.float32, device=S.device)
-        _lib.check(self.lib.dcs_istft(self.handle, _ptr(S), nsrc, T, ldf, T * ldf, _ptr(out), n, n, _stream_ptr(stream)))
+        _lib.check(self.lib.dcs_istft(self.handle, _ptr(S), nsrc, T, ldf, T * ldf, _ptr(out), n, n, _stream_ptr(stream, self.device)))
         return out
 
     def inverse_polar(self, mag, phase, mag_scale=1.0, num_out=None, stream=None):
@@ -159,7 +167,7 @@ class Stft(object):
         n = self.out_length(T) if num_out is None else int(num_out)
         out = torch.empty((n,), dtype=torch.float32, device=mag.device)
         _lib.check(self.lib.dcs_istft_polar(self.handle, self.ctx.handle, _ptr(mag), _ptr(phase), float(mag_scale), T, ldf,
-                                            _ptr(out), n, _stream_ptr(stream)))
+                                            _ptr(out), n, _stream_ptr(stream, self.device)))
         return out
 
     def close(self):
@@ -241,7 +249,7 @@ class Separator(object):
         assert out.dtype == np.float32 and out.shape == (self.nsrc, L) and out.flags.c_contiguous
         _lib.check(self.lib.dcs_separate_host(self.ctx.handle, self.model.handle, self.stft.handle, a.ctypes.data, L,
                                               self.scale_factor, self.overlap, self.patcher, out.ctypes.data, L,
-                                              _stream_ptr()))
+                                              _stream_ptr(None, self.ctx.device)))
         return out
 
     def separate_pcm16(self, pcm, downmix=1, out=None):
@@ -253,7 +261,7 @@ class Separator(object):
             out = np.empty((self.nsrc, L), dtype=np.int16)
         _lib.check(self.lib.dcs_separate_pcm16_host(self.ctx.handle, self.model.handle, self.stft.handle, p.ctypes.data, L,
                                                     ch, int(downmix if ch > 1 else 0), self.scale_factor, self.overlap,
-                                                    self.patcher, out.ctypes.data, L, _stream_ptr()))
+                                                    self.patcher, out.ctypes.data, L, _stream_ptr(None, self.ctx.device)))
         return out
 
     # ---- device buffers (torch tensors) ----
@@ -265,29 +273,33 @@ class Separator(object):
             out = torch.empty((self.nsrc, L), dtype=torch.float32, device=audio.device)
         _lib.check(self.lib.dcs_separate_audio(self.ctx.handle, self.model.handle, self.stft.handle, _ptr(audio), L,
                                                self.scale_factor, self.overlap, self.patcher, _ptr(out), out.stride(0),
-                                               _stream_ptr(stream)))
+                                               _stream_ptr(stream, self.ctx.device)))
         return out
 
     def separate_score(self, audio, filters, out=None, stream=None):
         """Score-informed Bach10: audio float [L] (numpy or cuda tensor) + normalised score filters
-        [4, T, F] float32 (deepconvsep_b200.score.score_filters) -> stems float32 [4, L] (same kind as
-        `audio`).  The filters are uploaded, the four input channels are formed on the device."""
+        [4, T, F] float32 (deepconvsep_b200.score.score_filters; or a cuda tensor [4, T, ldf] already on the
+        device) -> stems float32 [4, L] (same kind as `audio`).  The four input channels are formed on the device."""
         import torch
         host = not hasattr(audio, "is_cuda")
-        x = torch.as_tensor(np.ascontiguousarray(audio, dtype=np.float32), device="cuda") if host else audio
+        x = torch.as_tensor(np.ascontiguousarray(audio, dtype=np.float32), device=self.stft.dev) if host else audio
         L = x.numel()
         T = self.stft.num_frames(L)
-        f = np.asarray(filters, dtype=np.float32)
-        assert f.shape == (4, T, self.model.F), (f.shape, (4, T, self.model.F))
-        fd = torch.zeros((4, T, self.stft.ldf), dtype=torch.float32, device=x.device)
-        fd[:, :, :self.model.F] = torch.as_tensor(f, device=x.device)
+        if hasattr(filters, "is_cuda"):      # already on the device, padded rows: [4, T, ldf] float32
+            fd = filters
+            assert fd.is_cuda and fd.dtype == torch.float32 and fd.is_contiguous() and tuple(fd.shape) == (4, T, self.stft.ldf)
+        else:
+            f = np.asarray(filters, dtype=np.float32)
+            assert f.shape == (4, T, self.model.F), (f.shape, (4, T, self.model.F))
+            fd = torch.zeros((4, T, self.stft.ldf), dtype=torch.float32, device=x.device)
+            fd[:, :, :self.model.F] = torch.as_tensor(f, device=x.device)
         if out is None or host:
             outd = torch.empty((self.nsrc, L), dtype=torch.float32, device=x.device)
         else:
             outd = out
         _lib.check(self.lib.dcs_separate_audio_score(self.ctx.handle, self.model.handle, self.stft.handle, _ptr(x), L,
                                                      _ptr(fd), self.scale_factor, self.overlap, self.patcher, _ptr(outd),
-                                                     outd.stride(0), _stream_ptr(stream)))
+                                                     outd.stride(0), _stream_ptr(stream, self.ctx.device)))
         return outd.cpu().numpy() if host else outd
 
     def separate_stereo(self, audio, out=None, stream=None):
@@ -299,7 +311,7 @@ class Separator(object):
         if host:
             a = np.asarray(audio, dtype=np.float32)
             assert a.ndim == 2 and a.shape[1] == 2, a.shape
-            x = torch.as_tensor(np.ascontiguousarray(a.T), device="cuda")
+            x = torch.as_tensor(np.ascontiguousarray(a.T), device=self.stft.dev)
         else:
             x = audio.contiguous()
             assert x.dim() == 2 and x.shape[0] == 2 and x.dtype == torch.float32
@@ -307,10 +319,42 @@ class Separator(object):
         outd = out if (out is not None and not host) else torch.empty((self.nsrc * 2, L), dtype=torch.float32, device=x.device)
         _lib.check(self.lib.dcs_separate_audio_stereo(self.ctx.handle, self.model.handle, self.stft.handle, _ptr(x), x.stride(0), L,
                                                       self.scale_factor, self.overlap, self.patcher, _ptr(outd), outd.stride(0),
-                                                      _stream_ptr(stream)))
+                                                      _stream_ptr(stream, self.ctx.device)))
         if not host:
             return outd
         return np.ascontiguousarray(outd.cpu().numpy().reshape(self.nsrc, 2, L).transpose(2, 0, 1))
+
+    def separate_tapped(self, audio, filters=None, pool=False):
+        """Parity-test entry: the same pipeline as separate() / separate_score() / separate_stereo() with
+        the spectrum tap on (dcs_set_spectrum_tap) -> (stems as that call returns them, masked spectra
+        complex64 numpy [nplanes, T, F] -- the tensors the inverse STFT of THIS call consumed).
+        pool=True (max-pool net): also the tie bits uint8 [T, WP, 32] of this call (dcs_set_pool_tap)."""
+        import torch
+        a = np.asarray(audio)
+        L = a.shape[0]
+        T = self.stft.num_frames(L)
+        nplanes = self.nsrc * (2 if self.model.arch == "dsd_ild" else 1)
+        tap = torch.zeros((nplanes, T, self.stft.ldf), dtype=torch.complex64, device=self.stft.dev)
+        _lib.check(self.lib.dcs_set_spectrum_tap(self.ctx.handle, _ptr(tap), tap.numel()))
+        bits = None
+        if pool:
+            assert self.model.arch == "ikala", "only the max-pool network has routing decisions to tap"
+            WP = ((self.model.F - 30) // 3 + 1) // 4
+            bits = torch.zeros((T, WP, 32), dtype=torch.uint8, device=self.stft.dev)
+            _lib.check(self.lib.dcs_set_pool_tap(self.ctx.handle, _ptr(bits), bits.numel()))
+        try:
+            if self.model.arch == "bach10_score":
+                out = self.separate_score(a, filters)
+            elif self.model.arch == "dsd_ild":
+                out = self.separate_stereo(a)
+            else:
+                out = self.separate(a)
+            torch.cuda.synchronize(self.stft.dev)
+        finally:
+            _lib.check(self.lib.dcs_set_spectrum_tap(self.ctx.handle, None, 0))
+            _lib.check(self.lib.dcs_set_pool_tap(self.ctx.handle, None, 0))
+        S = tap[:, :, :self.model.F].cpu().numpy()
+        return (out, S, bits.cpu().numpy()) if pool else (out, S)
 
     def separate_spec(self, mag, X, stream=None):
         """scaled magnitude [T, ldf] + mixture STFT [T, ldf] -> masked spectra complex64 [nsrc, T, ldf]"""
@@ -318,7 +362,7 @@ class Separator(object):
         T, ldf = mag.shape
         S = torch.empty((self.nsrc, T, ldf), dtype=torch.complex64, device=mag.device)
         _lib.check(self.lib.dcs_separate_spec(self.ctx.handle, self.model.handle, _ptr(mag), _ptr(X), T, ldf, self.overlap,
-                                              self.patcher, _ptr(S), T * ldf, _stream_ptr(stream)))
+                                              self.patcher, _ptr(S), T * ldf, _stream_ptr(stream, self.ctx.device)))
         return S
 
     def num_patches(self, T):

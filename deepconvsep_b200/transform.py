@@ -20,13 +20,22 @@ _ctx = {}
 _plans = {}
 
 
-def _context(device=0):
+def _context(device=None):
+    """One libdcs context per device; None = torch's current device (under torchrun each rank has
+    called torch.cuda.set_device(local_rank): the plan, the tensors and the stream must all live
+    on THAT device)."""
+    if device is None:
+        import torch
+        device = torch.cuda.current_device()
     if device not in _ctx:
         _ctx[device] = engine.Context(device)
     return _ctx[device]
 
 
-def _plan(window, hop, nfft, syn_window=None, device=0):
+def _plan(window, hop, nfft, syn_window=None, device=None):
+    if device is None:
+        import torch
+        device = torch.cuda.current_device()
     w = np.ascontiguousarray(window, dtype=np.float64)
     n = int(nfft)
     if w.size != n:
@@ -51,7 +60,7 @@ def stft_norm(data, window=None, hopsize=256.0, nfft=2048.0, fs=44100.0):
     if window is None:
         window = sinebell(2048)
     st = _plan(window, hopsize, nfft)
-    x = torch.as_tensor(np.ascontiguousarray(data, dtype=np.float32), device="cuda")
+    x = torch.as_tensor(np.ascontiguousarray(data, dtype=np.float32), device=st.dev)
     X, _ = st.forward(x, want_mag=False)
     return X[:, :st.F].cpu().numpy().astype(np.complex128)
 
@@ -68,8 +77,8 @@ def istft_norm(X, window=None, analysisWindow=None, hopsize=256.0, nfft=2048.0):
     T, F = Xc.shape
     if F != st.F:
         raise ValueError("spectrogram has %d bins, nfft=%d needs %d" % (F, int(nfft), st.F))
-    S = torch.zeros((1, T, st.ldf), dtype=torch.complex64, device="cuda")
-    S[0, :, :F] = torch.as_tensor(Xc, device="cuda")
+    S = torch.zeros((1, T, st.ldf), dtype=torch.complex64, device=st.dev)
+    S[0, :, :F] = torch.as_tensor(Xc, device=st.dev)
     return st.inverse(S)[0].cpu().numpy().astype(np.float64)
 
 
@@ -155,7 +164,7 @@ class transformFFT(Transforms):
         """mag = |STFT| / sqrt(frameSize) [, ph = angle(STFT)]   (transform.py:224-252)"""
         import torch
         st = _plan(self.window, self.hopSize, self.frameSize)
-        x = torch.as_tensor(np.ascontiguousarray(audio, dtype=np.float32), device="cuda")
+        x = torch.as_tensor(np.ascontiguousarray(audio, dtype=np.float32), device=st.dev)
         if phase:
             mag, ph = st.forward_polar(x)
             return (mag[:, :st.F].cpu().numpy().astype(np.float64), ph[:, :st.F].cpu().numpy().astype(np.float64))
@@ -167,8 +176,8 @@ class transformFFT(Transforms):
         import torch
         st = _plan(self.window, self.hopSize, self.frameSize)
         T, F = mag.shape
-        m = torch.zeros((T, st.ldf), dtype=torch.float32, device="cuda")
-        p = torch.zeros((T, st.ldf), dtype=torch.float32, device="cuda")
-        m[:, :F] = torch.as_tensor(np.ascontiguousarray(mag, dtype=np.float32), device="cuda")
-        p[:, :F] = torch.as_tensor(np.ascontiguousarray(phase, dtype=np.float32), device="cuda")
+        m = torch.zeros((T, st.ldf), dtype=torch.float32, device=st.dev)
+        p = torch.zeros((T, st.ldf), dtype=torch.float32, device=st.dev)
+        m[:, :F] = torch.as_tensor(np.ascontiguousarray(mag, dtype=np.float32), device=st.dev)
+        p[:, :F] = torch.as_tensor(np.ascontiguousarray(phase, dtype=np.float32), device=st.dev)
         return st.inverse_polar(m, p).cpu().numpy().astype(np.float64)

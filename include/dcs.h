@@ -70,6 +70,19 @@ int64_t dcs_workspace_bytes(const dcs_ctx* ctx);
 /* number of kernels this library has launched through `ctx` since creation */
 int64_t dcs_launch_count(const dcs_ctx* ctx);
 
+/* Inspection tap (used by the parity tests): while set, every dcs_separate_audio* / *_host call on this ctx
+ * also copies the blended masked spectra its inverse STFT consumed -- complex[nplanes][T][ldf],
+ * ldf = dcs_padded_bins(N), nplanes = nsrc (x 2 channels for the stereo net) -- to d_S (capacity in
+ * elements; the call fails if it is too small).  d_S = NULL switches it off.  These are the tensors
+ * `overlapadd_multi(...)/scale * exp(j*phase)` of separate_dsd.py:301-304. */
+int dcs_set_spectrum_tap(dcs_ctx* ctx, dcs_complex* d_S, int64_t capacity);
+/* Same for the max-pool network (DCS_ARCH_IKALA): the tie bits of MaxPool2DLayer((1,4)) the un-pool
+ * (InverseLayer(pool), separate_ikala.py:183,188) routes by -- uint8[T][WP][32], bit r set: position 4*jp+r
+ * of the window equals its maximum, channel = last index (30 used), WP = ((F-30)/3+1)/4.  The routing is
+ * a discrete decision of the reference's graph; the parity tests adopt the device's where float64 flags
+ * the window as ill-conditioned and require agreement elsewhere.  capacity in bytes; NULL = off. */
+int dcs_set_pool_tap(dcs_ctx* ctx, uint8_t* d_bits, int64_t capacity);
+
 /* per-stage device timing (CUDA events on the launching stream): enable, run, synchronise the
  * stream, then read.  dcs_profile_read writes up to max_n durations (ms) and the stage names
  * joined by '\n' into names_buf, clears the records and returns the number of records. */

@@ -154,13 +154,34 @@ def maxpool_w(x, pw):
     return x[:, :, :, :wp * pw].reshape(B, C, H, wp, pw).max(axis=4)
 
 
-def maxpool_w_inverse(g, x, pw):
+def maxpool_w_inverse(g, x, pw, dev_hits=None, tau_rel=4e-6, stats=None):
     """InverseLayer(g, pool): Theano MaxPoolGrad -- the value goes to every position of the
-    window equal to the window maximum (ties all receive it); dropped border columns get 0."""
+    window equal to the window maximum (ties all receive it); dropped border columns get 0.
+
+    The routing is a DISCRETE decision: where two positions of a window differ by less than the rounding
+    noise of any float32 evaluation (or of the float32 STFT feeding it) the argmax is ill-conditioned --
+    the same kind of discontinuity as the soft mask's (near_kink).  For the parity tests `dev_hits` =
+    (hits [B,C,H,wp,pw], valid [B,1,H,1,1]) (the device's own tie bits per patch row) may be supplied: in windows where some non-maximal position
+    lies within tau of the maximum (tau = tau_rel * (|max| + 0.05)) the device's choice is adopted --
+    after checking it only selects positions inside that near-maximal set -- and everywhere else the
+    float64 argmax is used and the device is REQUIRED to agree (`stats` collects the counts)."""
     B, C, H, W = x.shape
     wp = W // pw
     xr = x[:, :, :, :wp * pw].reshape(B, C, H, wp, pw)
-    hit = (xr == xr.max(axis=4, keepdims=True))
+    top = xr.max(axis=4, keepdims=True)
+    hit = (xr == top)
+    if dev_hits is not None:
+        near = (top - xr) <= tau_rel * (np.abs(top) + 0.05)
+        amb = near.sum(axis=4, keepdims=True) > hit.sum(axis=4, keepdims=True)     # an ill-conditioned window
+        dev, valid = dev_hits
+        dev = np.where(valid, dev.astype(bool), hit)      # rows without a device decision keep the float64 one
+        if stats is not None:
+            stats["windows"] = stats.get("windows", 0) + int(amb.size)
+            stats["ambiguous"] = stats.get("ambiguous", 0) + int(amb.sum())
+            stats["disagree_well_conditioned"] = stats.get("disagree_well_conditioned", 0) + int(((dev != hit).any(axis=4, keepdims=True) & ~amb).sum())
+            stats["inadmissible"] = stats.get("inadmissible", 0) + int(((dev & ~near).any(axis=4, keepdims=True) & amb).sum()) \
+                + int((~dev.any(axis=4, keepdims=True) & amb).sum())
+        hit = np.where(amb, dev, hit)
     gx = np.zeros_like(x)
     gx[:, :, :, :wp * pw] = (hit * g[..., None]).reshape(B, C, H, wp * pw)
     return gx
@@ -171,11 +192,25 @@ def relu(x):
 
 
 # ----------------------------------------------------------------------------- networks
-def predict(params, x, arch, return_pre=False):
+_F64_CACHE = {"key": None, "val": None}
+
+
+def _as_float64(params):
+    """float64 copies of a parameter list, kept for the last list seen (the Bach10 nets have 214 M
+    parameters: converting them once per 32-patch batch dominated the oracle's run time)."""
+    key = tuple((id(v), getattr(v, "shape", None)) for v in params)
+    if _F64_CACHE["key"] != key:
+        _F64_CACHE["val"] = [np.asarray(v, dtype=np.float64) for v in params]
+        _F64_CACHE["key"] = key
+    return _F64_CACHE["val"]
+
+
+def predict(params, x, arch, return_pre=False, pool_dev=None, pool_stats=None):
     """`lasagne.layers.get_output(build_ca(...), deterministic=True)`: x [B,nch,tc,F] ->
-    rectified concat output [B, nout, tc, F] (return_pre: the value before the final rectify)."""
+    rectified concat output [B, nout, tc, F] (return_pre: the value before the final rectify).
+    pool_dev: see maxpool_w_inverse (parity tests of the max-pool net only)."""
     a = ARCHS[arch]
-    p = [np.asarray(v, dtype=np.float64) for v in params]
+    p = _as_float64(params)
     x = np.asarray(x, dtype=np.float64)
     B, nch, tc, F = x.shape
     d = arch_dims(arch, F, tc)
@@ -191,7 +226,7 @@ def predict(params, x, arch, return_pre=False):
         r = relu(z @ Ws + bs).reshape(B, d["f2"], d["h2"], d["w2"])      # DenseLayer + Reshape
         g = conv2d_inverse(r, W2, hp.shape)                              # InverseLayer(., conv2)
         if a["pool"]:
-            g = maxpool_w_inverse(g, h1, a["pool"])                      # InverseLayer(., pool1)
+            g = maxpool_w_inverse(g, h1, a["pool"], dev_hits=pool_dev, stats=pool_stats)   # InverseLayer(., pool1)
         decs.append(conv2d_inverse(g, W1, x.shape, s1))                  # InverseLayer(., conv1)
     merged = np.concatenate([decs[i] for i in a["dec_of_out"]], axis=1)  # ConcatLayer(axis=1)
     pre = merged + p[-1][None, :, None, None]                            # BiasLayer
@@ -244,7 +279,7 @@ def predict_function2(params, x, arch, rand=None, pred=None):
     return [m[:, i:i + 1] * mix for i in range(a["nsrc"])]
 
 
-def predict_function_ild(params, x, rand=None):
+def predict_function_ild(params, x, rand=None, pred=None):
     """`predict_function` of the stereo / ILD trainer (trainCNN_ILD_DSD100.py:176-189,232):
     x [B, 2, tc, F] -> list over the input channels j of [B, nsrc, tc, F] = mask_j * x[:, j].
     The network's outputs are ordered (source, channel); channel j's masks are outputs j::nch
@@ -253,7 +288,8 @@ def predict_function_ild(params, x, rand=None):
     additive eps * noise on the estimate, 1e-13 absolute)."""
     a = ARCHS["dsd_ild"]
     x = np.asarray(x, dtype=np.float64)
-    pred = predict(params, x, "dsd_ild")
+    if pred is None:
+        pred = predict(params, x, "dsd_ild")
     nch, nsrc = a["nch"], a["nsrc"]
     out = []
     for j in range(nch):

@@ -30,9 +30,11 @@ def decode_wav_array(audioObj, family="dsd"):
 
 def separate(audio, params, arch, frameSize=1024, hopSize=512, window=np.hanning,
              scale_factor=0.3, time_context=30, overlap=25, batch_size=32,
-             patcher="standalone", return_spec=False, count_kinks=False):
-    """mono float64 audio [L] (or, for arch 'bach10_score', a callable building the 4-channel
-    input from the scaled magnitude) -> stems float64 [nsrc, L]."""
+             patcher="standalone", return_spec=False, count_kinks=False, pool_bits=None):
+    """mono float64 audio [L] -> stems float64 [nsrc, L].
+    pool_bits (max-pool net, parity tests only): the device's tie bits uint8 [T, WP, C>=30] (bit r: position
+    4*jp+r of the window received the value); adopted in ill-conditioned windows only, see
+    nets.maxpool_w_inverse; separate.last_pool_stats holds the counts."""
     a = nets.ARCHS[arch]
     mag, ph = dsp.compute_file(audio, phase=True, frameSize=frameSize, hopSize=hopSize,
                                window=window)
@@ -40,7 +42,33 @@ def separate(audio, params, arch, frameSize=1024, hopSize=512, window=np.hanning
     gen = patch.generate_overlapadd if patcher == "standalone" else patch.generate_overlapadd_util
     batches, nchunks = gen(mag, input_size=mag.shape[-1], time_context=time_context,
                            overlap=overlap, batch_size=batch_size)
-    pres = [nets.predict(params, b, arch, return_pre=True) for b in batches] if count_kinks else None
+    pool_stats = {}
+    if pool_bits is not None:
+        # per-frame device decisions -> per-patch [B, C, tc, wp, 4]; frames beyond T (zero padding) and the unused
+        # tail of the last batch keep the float64 decision (their input is exactly constant)
+        step_, T_ = time_context - overlap, mag.shape[0]
+        bits = np.asarray(pool_bits)[:, :, :30]
+        dev_frames = np.stack([(bits >> r) & 1 for r in range(4)], axis=-1).astype(bool)       # [T, WP, C, 4]
+        dev_frames = dev_frames.transpose(2, 0, 1, 3)                                         # [C, T, WP, 4]
+
+        def dev_hits_of(bi, b):
+            C_, T2, WP_, _ = dev_frames.shape
+            out = np.zeros((b.shape[0], C_, time_context, WP_, 4), dtype=bool)
+            valid = np.zeros((b.shape[0], 1, time_context, 1, 1), dtype=bool)
+            for i in range(b.shape[0]):
+                k = bi * batch_size + i
+                if k >= nchunks:
+                    break
+                t0 = k * step_
+                n = max(0, min(time_context, T_ - t0, T2 - t0))
+                out[i, :, :n] = dev_frames[:, t0:t0 + n]
+                valid[i, 0, :n] = True
+            return out, valid
+        pres = [nets.predict(params, b, arch, return_pre=True, pool_dev=dev_hits_of(bi, b), pool_stats=pool_stats)
+                for bi, b in enumerate(batches)]
+    else:
+        pres = [nets.predict(params, b, arch, return_pre=True) for b in batches] if count_kinks else None
+    separate.last_pool_stats = pool_stats
     output = [nets.predict_function2(params, b, arch, pred=None if pres is None else nets.relu(pres[i]))
               for i, b in enumerate(batches)]
     output = np.array(output)                            # [nb, nsrc, B, 1, tc, F]
@@ -135,12 +163,13 @@ def separate_score(audio, filters, params, frameSize=4096, hopSize=512, window=N
 
 
 def separate_stereo(audio, params, frameSize=1024, hopSize=512, window=np.hanning, scale_factor=0.3,
-                    time_context=30, overlap=25, batch_size=32, count_kinks=False):
+                    time_context=30, overlap=25, batch_size=32, count_kinks=False, return_spec=False):
     """Separation loop of the stereo / ILD trainer (trainCNN_ILD_DSD100.py:299-327):
     audio float64 [L, 2] -> stems float64 [L, nsrc, 2] (`sep_audio`).  One STFT per channel
     (`compute_transform`), util's zero-padded patcher on the [2, T, F] tensor, one network pass per
     batch, then per channel the 4-source cross-fade and one iSTFT per (source, channel) with that
-    channel's mixture phase."""
+    channel's mixture phase.  return_spec: also (mag [nch,T,F], phases [nch][T,F], blended magnitudes
+    [nch][nsrc,T',F])."""
     a = nets.ARCHS["dsd_ild"]
     nch = audio.shape[1]
     mags, phs = [], []
@@ -151,23 +180,34 @@ def separate_stereo(audio, params, frameSize=1024, hopSize=512, window=np.hannin
     mag = scale_factor * np.stack(mags).astype(np.float32)  # :304
     batches, nchunks = patch.generate_overlapadd_util(mag, input_size=mag.shape[-1], time_context=time_context,
                                                       overlap=overlap, batch_size=batch_size)
-    output = np.array([nets.predict_function_ild(params, b) for b in batches])   # [nb, nch, B, nsrc, tc, F]
+    pres = [nets.predict(params, b, "dsd_ild", return_pre=True) for b in batches] if count_kinks else None
+    output = np.array([nets.predict_function_ild(params, b, pred=None if pres is None else nets.relu(pres[i]))
+                       for i, b in enumerate(batches)])   # [nb, nch, B, nsrc, tc, F]
     kink_energy = np.zeros(nch)
     if count_kinks:     # bins whose mask sits on its discontinuity (all outputs of a channel vanish), see separate()
         nk, left = 0, nchunks
-        for b in batches:
+        step = time_context - overlap
+        T = phs[0].shape[0]
+        kmap = np.zeros((nch, max(T, nchunks * step + time_context), mag.shape[-1]), dtype=bool)
+        for bi, b in enumerate(batches):
             nb = max(0, min(left, batch_size))
-            pre = nets.predict(params, b, "dsd_ild", return_pre=True)[:nb]
+            pre = pres[bi][:nb]
             for j in range(nch):
                 flag = nets.near_kink(pre[:, j::nch], a["mask"], a["nsrc"])
                 nk += int(flag.sum())
                 kink_energy[j] += float((flag * b[:nb, j] ** 2).sum())
+                for i in np.nonzero(flag.reshape(nb, -1).any(axis=1))[0]:
+                    k0 = (bi * batch_size + int(i)) * step
+                    kmap[j, k0:k0 + time_context] |= flag[i]
             left -= batch_size
         separate_stereo.last_kinks = nk
         separate_stereo.last_kink_bound = np.zeros((a["nsrc"], nch))
+        separate_stereo.last_kink_map = kmap[:, :T]
     sep = np.zeros((audio.shape[0], a["nsrc"], nch))
+    mms = []
     for j in range(nch):
         mm = patch.overlapadd_multi(np.swapaxes(output[:, j:j + 1], 1, 3), batches, nchunks, overlap=overlap)
+        mms.append(mm)
         if count_kinks:
             for i in range(a["nsrc"]):
                 separate_stereo.last_kink_bound[i, j] = float(np.sqrt(kink_energy[j] / max(float((mm[i] ** 2).sum()), 1e-300)))
@@ -175,6 +215,8 @@ def separate_stereo(audio, params, frameSize=1024, hopSize=512, window=np.hannin
             audio_out = dsp.compute_inverse(mm[i, :phs[j].shape[0]] / scale_factor, phs[j], frameSize=frameSize,
                                             hopSize=hopSize, window=window)
             sep[:, i, j] = audio_out[:audio.shape[0]]
+    if return_spec:
+        return sep, mag, phs, mms
     return sep
 
 

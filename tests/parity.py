@@ -94,7 +94,8 @@ def strict_check(name, got, S_dev, want, mag, ph, mm, kmap, N, hop, window, scal
                rel_l2=errs, rel_l2_unmodified=raw, rel_l2_spectrum_flagged_excluded=spec, tol=tol)
     if extra:
         rec.update(extra)
-    record(name, **rec)
+    if name:
+        record(name, **rec)
     for s in range(nsrc):
         assert errs[s] <= tol, (name, s, errs[s], raw[s], nflag)
         assert spec[s] <= tol, (name, "spectrum", s, spec[s])
