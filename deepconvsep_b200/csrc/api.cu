@@ -417,12 +417,12 @@ static int dsd_forward(dcs_ctx* ctx, dcs_model* m, const float* d_mag, int64_t m
   DCS_TRY(ensure_layout(ctx, 1, (size_t)(Tp - kh2 + 1) * C2p * 4, sig, st));
   DCS_TRY(ensure_layout(ctx, 2, (size_t)P * nfc * 4, sig, st));
   DCS_TRY(ensure_layout(ctx, 3, (size_t)P * ndec * HP * C2p * 4, sig, st));
-  // G: the transposed conv2 output.  For the tensor-core mask kernel (the 3-decoder DSD100 net) it is
-  // stored frame-major ([T][6 slots][3 decoders][ldg], GemmDesc fm_*) so that a group of frames is one
+  // G: the transposed conv2 output.  For the tensor-core mask kernel it is
+  // stored frame-major ([T][6 slots][ndec decoders][ldg], GemmDesc fm_*) so that a group of frames is one
   // TMA box; the FFMA mask kernel reads the patch-major [P][ndec][tc][ldg] order.  Unwritten slots must
   // stay zero / finite: the layout kind is part of the signature, so switching re-zeroes the buffer.
-  const bool mask_tc = !ctx->debug_simt_gemm && ndec == 3 && nch == 1 && (tc + step - 1) / step <= 6;
-  const size_t g_rows = mask_tc ? (size_t)T * 6 * 3 : (size_t)P * ndec * tc;
+  const bool mask_tc = !ctx->debug_simt_gemm && (tc + step - 1) / step <= 6;
+  const size_t g_rows = mask_tc ? (size_t)T * 6 * ndec : (size_t)P * ndec * tc;
   DCS_TRY(ensure_layout(ctx, 4, g_rows * ldg * 4, sig ^ (mask_tc ? 0x5a5a : 0), st));
   float *H1 = bH1.as<float>(), *H2 = bH2.as<float>(), *z = bz.as<float>(), *ap = bap.as<float>(), *G = bG.as<float>();
 
@@ -448,7 +448,7 @@ static int dsd_forward(dcs_ctx* ctx, dcs_model* m, const float* d_mag, int64_t m
   g5.m_inner = (int)(P * ndec); g5.a_so = C2p; g5.a_si = (int64_t)HP * C2p;
   g5.cm_inner = (int)(P * ndec); g5.c_so = ldg; g5.c_si = (int64_t)tc * ldg;
   g5.kc_rows = (int)(P * ndec); g5.kc_unit = C2p; g5.kc_pad = kh2 - 1; g5.kc_n = h2; g5.kc_taps = kh2;
-  if (mask_tc) { g5.fm_step = step; g5.fm_tc = tc; g5.fm_T = (int)T; g5.fm_slots = 6; g5.fm_ndec = 3; }
+  if (mask_tc) { g5.fm_step = step; g5.fm_tc = tc; g5.fm_T = (int)T; g5.fm_slots = 6; g5.fm_ndec = ndec; }
   { ProfScope ps(ctx, "dec_convT2_gemm", st); DCS_TRY(run_gemm(ctx, g5, m->tWt2, st)); }
   // InverseLayer(conv1) + bias + ReLU + mask + cross-fade + phase; the stereo net: once per channel
   // with that channel's conv1 weights, output biases and mixture STFT (trainCNN_ILD_DSD100.py:183-186)
@@ -463,7 +463,7 @@ static int dsd_forward(dcs_ctx* ctx, dcs_model* m, const float* d_mag, int64_t m
       DCS_REQUIRE(dsd_mask_tc_supported(a), "dsd_forward: tensor-core mask kernel does not take this shape");
       DCS_TRY(launch_dsd_mask_tc(ctx, a, st));
     } else {
-      DCS_TRY(launch_dsd_mask(ctx, a, st));   // FFMA kernel: > 6 patches per frame, the 4-decoder net, bring-up cross-check
+      DCS_TRY(launch_dsd_mask(ctx, a, st));   // FFMA kernel: > 6 patches per frame, bring-up cross-check
     }
   }
   return DCS_OK;

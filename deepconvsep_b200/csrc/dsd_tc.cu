@@ -7,7 +7,7 @@
 // GEMM view (D = A * B^T, fp32-accurate 3xTF32):
 //   M = frequency bins  -> TMEM lanes (one epilogue thread per bin; its 18 values per frame are
 //                           thread-local, so mask + cross-fade need no shuffles)
-//   N = (frame, patch slot, decoder) = 8 x 6 x 3 = 144 columns per tile
+//   N = (frame, patch slot, decoder) = 8 x 6 x 3 (or 6 x 6 x 4, the stereo net) = 144 columns per tile
 //   K = conv1 filters (50, padded to 56 = 7 k-steps)
 //   A = W1t tile [128 bins][K]  (weights; split hi/lo into shared memory ONCE per CTA)
 //   B = G rows   [144][K]       (decoder activations).  The transposed conv2 writes G frame-major
@@ -30,28 +30,40 @@ namespace dcs {
 using namespace tc;
 
 constexpr int MT_BINS = 128;             // bins per CTA tile
-constexpr int MT_FRAMES = 8;             // frames per group
 constexpr int MT_SLOTS = 6;              // patch slots per frame
-constexpr int MT_COLS = MT_FRAMES * MT_SLOTS * 3;  // 144
+constexpr int MT_COLS = 144;             // GEMM columns per group = frames x 6 slots x decoders
 constexpr int MT_C1 = 50;
 constexpr int MT_KSTEPS = 7;             // ceil(50 / 8)
-constexpr int MT_EPI_WARPS = 16;          // 4 per TMEM lane quadrant, 2 frames of a group each
-constexpr int MT_TMA_WARP = MT_EPI_WARPS + 1;
 constexpr int MT_SPLIT_WARPS = 4;
 constexpr int MT_SPLIT = MT_SPLIT_WARPS * 32;            // 128 low-plane threads
-constexpr int MT_THREADS = (MT_EPI_WARPS + 2 + MT_SPLIT_WARPS) * 32;  // 704
 constexpr int MT_A_SUB = MT_BINS * ROW_BYTES;      // 16 KB: [128][32] fp32
 constexpr int MT_B_SUB = MT_COLS * ROW_BYTES;      // 18 KB: [144][32] fp32
 constexpr int MT_A_BYTES = 4 * MT_A_SUB;           // hi k0-31, hi k32-63, lo k0-31, lo k32-63
 constexpr int MT_B_STAGE = 4 * MT_B_SUB;           // same four planes
 constexpr int MT_BAR_OFF = MT_A_BYTES + 2 * MT_B_STAGE;
 constexpr int MT_XF_OFF = MT_BAR_OFF + 128;        // cross-fade coefficient tables, 12 float4 per epilogue warp
-constexpr int MT_SMEM = MT_XF_OFF + MT_EPI_WARPS * 12 * 16 + 1024;  // + alignment slack
+constexpr int MT_SMEM = MT_XF_OFF + 16 * 12 * 16 + 1024;  // + alignment slack
 constexpr uint32_t MT_TMEM_COLS = 512;
 
-__global__ void __launch_bounds__(MT_THREADS, 1)
+// NDEC = 3: the DSD100 / hiphopss net (4th output = decoder 2 with its own bias, all-zero bins get 1/4 each,
+//           separate_dsd.py:228,258-266), 8 frames per group;
+// NDEC = 4: the stereo / ILD net, one launch per input channel (one decoder per source, all-zero bins get 0,
+//           trainCNN_ILD_DSD100.py:99-106,183-186), 6 frames per group -- the same 144-column tile either way.
+template <int NDEC>
+struct MaskTile {
+  static constexpr int FRAMES = MT_COLS / (MT_SLOTS * NDEC);    // 8 or 6
+  static constexpr int EPI_WARPS = 2 * FRAMES;                  // 4 TMEM lane quadrants x FRAMES/2 frame pairs
+  static constexpr int TMA_WARP = EPI_WARPS + 1;
+  static constexpr int THREADS = (EPI_WARPS + 2 + MT_SPLIT_WARPS) * 32;   // 704 or 576
+  static constexpr int VALS = MT_SLOTS * NDEC;                  // accumulator columns per frame: 18 or 24
+};
+
+template <int NDEC>
+__global__ void __launch_bounds__(MaskTile<NDEC>::THREADS, 1)
 dsd_mask_tc_kernel(const DsdMaskArgs a, const __grid_constant__ CUtensorMap tmG, const float4* __restrict__ xtab,
                    int groups_per_cta, int num_groups) {
+  using MT = MaskTile<NDEC>;
+  constexpr int MT_FRAMES = MT::FRAMES, MT_EPI_WARPS = MT::EPI_WARPS, MT_TMA_WARP = MT::TMA_WARP, VALS = MT::VALS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = align1024(smem_raw);
   uint8_t* sA = smem;
@@ -198,12 +210,12 @@ dsd_mask_tc_kernel(const DsdMaskArgs a, const __grid_constant__ CUtensorMap tmG,
       __syncwarp();
       mbar_wait_relaxed(&tmem_full[s], (it >> 1) & 1);
       fence_after_sync();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + s * 256 + 36 * fsub;
-      float y[2][18];
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + s * 256 + 2 * VALS * fsub;
+      float y[2][VALS];
       tmem_ld16_nowait(taddr, y[0]);
-      tmem_ld2_nowait(taddr + 16, y[0] + 16);
-      tmem_ld16_nowait(taddr + 18, y[1]);
-      tmem_ld2_nowait(taddr + 34, y[1] + 16);
+      if (NDEC == 3) tmem_ld2_nowait(taddr + 16, y[0] + 16); else tmem_ld8_nowait(taddr + 16, y[0] + 16);
+      tmem_ld16_nowait(taddr + VALS, y[1]);
+      if (NDEC == 3) tmem_ld2_nowait(taddr + VALS + 16, y[1] + 16); else tmem_ld8_nowait(taddr + VALS + 16, y[1] + 16);
       tmem_wait_ld();
       // the accumulator values are in registers: hand the TMEM buffer back right away
       fence_before_sync();
@@ -216,14 +228,15 @@ dsd_mask_tc_kernel(const DsdMaskArgs a, const __grid_constant__ CUtensorMap tmG,
 #pragma unroll
         for (int ff = 0; ff < 2; ++ff) {
           const float4 c = xf[ff * 6 + j];   // (up, down, up/4, -)
-          const float p0 = fmaxf(y[ff][3 * j + 0] + bo0, 0.f), p1 = fmaxf(y[ff][3 * j + 1] + bo1, 0.f);
-          const float p2 = fmaxf(y[ff][3 * j + 2] + bo2, 0.f), p3 = fmaxf(y[ff][3 * j + 1] + bo3, 0.f);
+          const float p0 = fmaxf(y[ff][NDEC * j + 0] + bo0, 0.f), p1 = fmaxf(y[ff][NDEC * j + 1] + bo1, 0.f);
+          const float p2 = fmaxf(y[ff][NDEC * j + 2] + bo2, 0.f);
+          const float p3 = fmaxf(y[ff][NDEC * j + (NDEC == 3 ? 1 : 3)] + bo3, 0.f);   // DSD100: decoder 2 again (separate_dsd.py:228)
           const float tot = (p0 + p1) + (p2 + p3);
           const bool pos = tot > 1.2e-38f;
           float rc;
           asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(tot));
           const float r = pos ? c.x * rc : 0.f;        // up * mask = p * (up / tot)
-          const float q = pos ? 0.f : c.z;             // all-zero bin: 1/4 each
+          const float q = (pos || NDEC == 4) ? 0.f : c.z;   // all-zero bin: 1/4 each (DSD100 rule); 0 (ILD rule)
           acc[ff][0] = fmaf(c.y, acc[ff][0], fmaf(p0, r, q));
           acc[ff][1] = fmaf(c.y, acc[ff][1], fmaf(p1, r, q));
           acc[ff][2] = fmaf(c.y, acc[ff][2], fmaf(p2, r, q));
@@ -277,34 +290,41 @@ __global__ void dsd_xfade_table_kernel(float4* __restrict__ tab, int T, int Tpad
 
 bool dsd_mask_tc_supported(const DsdMaskArgs& a) {
   const int step = a.tc - a.overlap;
-  return step > 0 && (a.tc + step - 1) / step <= MT_SLOTS && a.ldg % 4 == 0 && a.ldg >= 52 && a.ldg <= 64 && ((uintptr_t)a.G % 16 == 0);
+  return step > 0 && (a.ndec == 3 || a.ndec == 4) && (a.tc + step - 1) / step <= MT_SLOTS && a.ldg % 4 == 0 && a.ldg >= 52 &&
+         a.ldg <= 64 && ((uintptr_t)a.G % 16 == 0);
 }
 
 // all F bins; the last 128-bin tile holds only the Nyquist bin (F = 2^k + 1)
-int launch_dsd_mask_tc(dcs_ctx* ctx, const DsdMaskArgs& a, cudaStream_t st) {
-  if (a.T <= 0) return DCS_OK;
-  DCS_REQUIRE(dsd_mask_tc_supported(a), "dsd_mask_tc: unsupported shape");
-  DCS_TRY(ensure_smem_attr(dsd_mask_tc_kernel, MT_SMEM));
+template <int NDEC>
+static int launch_dsd_mask_tc_t(dcs_ctx* ctx, const DsdMaskArgs& a, cudaStream_t st) {
+  using MT = MaskTile<NDEC>;
+  DCS_TRY(ensure_smem_attr(dsd_mask_tc_kernel<NDEC>, MT_SMEM));
   const int m_tiles = (a.F + MT_BINS - 1) / MT_BINS;
-  const int num_groups = (a.T + MT_FRAMES - 1) / MT_FRAMES;
+  const int num_groups = (a.T + MT::FRAMES - 1) / MT::FRAMES;
   int chunks = ctx->num_sms / m_tiles;
   if (chunks < 1) chunks = 1;
   if (chunks > num_groups) chunks = num_groups;
   const int gpc = (num_groups + chunks - 1) / chunks;
   dim3 grid((unsigned)m_tiles, (unsigned)((num_groups + gpc - 1) / gpc));
-  // G is frame-major here: [T * 6 slots * 3 decoders][ldg] (see GemmDesc fm_*)
+  // G is frame-major here: [T * 6 slots * NDEC decoders][ldg] (see GemmDesc fm_*)
   alignas(64) CUtensorMap tmG;
-  DCS_TRY(tma_encode_2d_f32(&tmG, a.G, (uint64_t)a.ldg, (uint64_t)a.T * MT_SLOTS * 3, (uint64_t)a.ldg * 4, MT_COLS));
-  const int Tpad = num_groups * MT_FRAMES;
+  DCS_TRY(tma_encode_2d_f32(&tmG, a.G, (uint64_t)a.ldg, (uint64_t)a.T * MT_SLOTS * NDEC, (uint64_t)a.ldg * 4, MT_COLS));
+  const int Tpad = num_groups * MT::FRAMES;
   DCS_TRY(ctx->net[11].ensure((size_t)Tpad * MT_SLOTS * sizeof(float4), st));
   float4* xtab = ctx->net[11].as<float4>();
   dsd_xfade_table_kernel<<<(unsigned)ceil_div64((int64_t)Tpad * MT_SLOTS, 256), 256, 0, st>>>(xtab, a.T, Tpad, a.P, a.tc, a.overlap);
   DCS_CHECK_LAUNCH();
   ctx->launches++;
-  dsd_mask_tc_kernel<<<grid, MT_THREADS, MT_SMEM, st>>>(a, tmG, xtab, gpc, num_groups);
+  dsd_mask_tc_kernel<NDEC><<<grid, MT::THREADS, MT_SMEM, st>>>(a, tmG, xtab, gpc, num_groups);
   DCS_CHECK_LAUNCH();
   ctx->launches++;
   return DCS_OK;
+}
+
+int launch_dsd_mask_tc(dcs_ctx* ctx, const DsdMaskArgs& a, cudaStream_t st) {
+  if (a.T <= 0) return DCS_OK;
+  DCS_REQUIRE(dsd_mask_tc_supported(a), "dsd_mask_tc: unsupported shape");
+  return a.ndec == 4 ? launch_dsd_mask_tc_t<4>(ctx, a, st) : launch_dsd_mask_tc_t<3>(ctx, a, st);
 }
 
 }  // namespace dcs

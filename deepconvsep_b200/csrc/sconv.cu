@@ -43,8 +43,9 @@ sconv_mask_kernel(const SconvMaskArgs a) {
   float* gs = sm;                                   // [NDEC][JT][33]
   float4* ws = reinterpret_cast<float4*>(sm + NDEC * JT * 33 + (4 - (NDEC * JT * 33) % 4) % 4);  // [NW][ND][32]
   const int tid = threadIdx.x;
-  const int m0 = blockIdx.x * SC_TILE, m = m0 + tid;
-  const int t = blockIdx.y;
+  // frames on gridDim.x (2^31-1 blocks: any clip length), bin tiles on gridDim.y (a handful)
+  const int m0 = blockIdx.y * SC_TILE, m = m0 + tid;
+  const int t = blockIdx.x;
   const int step = a.tc - a.overlap;
   // weights: w[dd][f][r] = W1[f][KW-1 - r - STRIDE*dd] (0 where the tap index is negative)
   for (int i = tid; i < NW * ND * 32; i += SC_TILE) ws[i] = reinterpret_cast<const float4*>(a.W)[i];
@@ -165,7 +166,7 @@ static int launch_sconv_t(dcs_ctx* ctx, const SconvMaskArgs& a, cudaStream_t st)
   const size_t smem = (size_t)(NDEC * JT * 33 + 4) * sizeof(float) + NW * ND * 32 * sizeof(float4);
   DCS_TRY(ensure_smem_attr(sconv_mask_kernel<STRIDE, ND, NSRC, NDEC, RULE, POOL, NW>, (int)smem));
   const int mtot = (a.F + STRIDE - 1) / STRIDE;
-  dim3 grid((unsigned)ceil_div64(mtot, SC_TILE), (unsigned)a.T);
+  dim3 grid((unsigned)a.T, (unsigned)ceil_div64(mtot, SC_TILE));
   sconv_mask_kernel<STRIDE, ND, NSRC, NDEC, RULE, POOL, NW><<<grid, SC_TILE, smem, st>>>(a);
   DCS_CHECK_LAUNCH();
   ctx->launches++;
@@ -174,7 +175,6 @@ static int launch_sconv_t(dcs_ctx* ctx, const SconvMaskArgs& a, cudaStream_t st)
 
 int launch_sconv_mask(dcs_ctx* ctx, const SconvMaskArgs& a, cudaStream_t st) {
   if (a.T <= 0) return DCS_OK;
-  DCS_REQUIRE(a.T <= 65535, "sconv_mask: clip too long (%d frames)", a.T);
   const int step = a.tc - a.overlap;
   DCS_REQUIRE(step > 0 && (a.tc + step - 1) / step <= 64, "sconv_mask: bad time_context/overlap");
   if (a.arch == DCS_ARCH_BACH10) return launch_sconv_t<4, 8, 4, 4, 1, 0, 1>(ctx, a, st);

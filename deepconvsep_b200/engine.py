@@ -187,10 +187,15 @@ class Model(object):
 
     def __init__(self, ctx, params, arch=None, feat_size=None, time_context=None):
         self.ctx, self.lib = ctx, ctx.lib
-        a, F, tc = infer_arch(params, feat_size) if arch is None else (arch, feat_size, time_context or 30)
-        if arch is not None and feat_size is None:
-            _, F, _ = infer_arch(params)
-        self.arch, self.F, self.tc = a, int(F), int(time_context or tc)
+        try:
+            ia, iF, itc = infer_arch(params, feat_size)   # time_context None: the one the weights were trained with
+        except ValueError:
+            if arch is None or feat_size is None:
+                raise
+            ia, iF, itc = arch, feat_size, 30
+        a = ia if arch is None else arch
+        F = feat_size if (arch is not None and feat_size is not None) else iF
+        self.arch, self.F, self.tc = a, int(F), int(time_context or itc)
         arrs = [np.ascontiguousarray(p, dtype=np.float32) for p in params]
         n = len(arrs)
         ptrs = (C.c_void_p * n)(*[x.ctypes.data for x in arrs])
@@ -221,7 +226,7 @@ class Separator(object):
     """train_auto() as an object: build once (weights uploaded, plan made), call many times."""
 
     def __init__(self, params, arch=None, frame_size=None, hop=None, window=None, scale_factor=0.3,
-                 time_context=30, overlap=None, patcher="standalone", device=0, feat_size=None):
+                 time_context=None, overlap=None, patcher="standalone", device=0, feat_size=None):
         self.ctx = Context(device)
         if arch is None and frame_size is not None and feat_size is None:
             feat_size = frame_size // 2 + 1

@@ -84,8 +84,12 @@ def ratios_from_lags(R, idx, n, flen):
                 SDR[jest, jtrue] = 10 * np.log10(p_j / np.maximum(e_se - p_j, zero))
                 SIR[jest, jtrue] = 10 * np.log10(p_j / np.maximum(p_all - p_j, zero))
                 SAR[jest, jtrue] = 10 * np.log10(p_all / np.maximum(e_se - p_all, zero))
-    best, perm = -np.inf, None
-    for p in itertools.permutations(range(n)):
+    # MATLAB: perm = perms(1:nsrc); [~, popt] = max(meanSIR) (bss_eval_sources.m:56-63).  perms() enumerates in
+    # reverse lexicographic order and max() returns the FIRST maximum -- also when every mean is NaN / -Inf
+    # (a silent reference or an all-zero estimate), where it returns index 1 instead of failing.
+    cands = sorted(itertools.permutations(range(n)), reverse=True)
+    best, perm = -np.inf, cands[0]
+    for p in cands:
         m = np.mean([SIR[p[j], j] for j in range(n)])
         if m > best:
             best, perm = m, p

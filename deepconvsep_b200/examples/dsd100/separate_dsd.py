@@ -5,7 +5,6 @@
 Same functions and signatures as the reference script; the work happens in the CUDA pipeline
 (STFT -> encoder/decoder -> soft mask + cross-fade -> iSTFT), the host only reads and writes wavs."""
 import sys
-import getopt
 import numpy as np
 
 from ...models import load_model                       # noqa: F401  (separate_dsd.py:17-21)
@@ -44,26 +43,13 @@ def train_auto(filein, outdir, model, scale_factor=0.3, time_context=30, overlap
 
 
 def main(argv):
-    try:
-        opts, args = getopt.getopt(argv, "hi:o:m:", ["ifile=", "odir=", "mfile="])
-    except getopt.GetoptError:
-        print(USAGE)
-        sys.exit(2)
-    inputfile = outdir = model = None
-    for opt, arg in opts:
-        if opt == '-h':
-            print(USAGE)
-            sys.exit()
-        elif opt in ("-i", "--ifile"):
-            inputfile = arg
-        elif opt in ("-o", "--odir"):
-            outdir = arg
-        elif opt in ("-m", "--mfile"):
-            model = arg
-    if inputfile is None or outdir is None or model is None:
-        print(USAGE)
-        sys.exit(2)
-    train_auto(inputfile, outdir, model, 0.3, 30, 25, 32, 513)      # separate_dsd.py:332
+    """`-i -o -m` as separate_dsd.py:316-332; extra long options: see _common.parse_cli."""
+    def run_one(f, o, m, N, w, dev, slot, several):
+        # several clips into one directory: keep them apart the way the iKala / Bach10 scripts name their outputs
+        name = (lambda fn, src: fn.replace(".wav", "_" + src + ".wav")) if several else (lambda fn, src: src + ".wav")
+        return _common.run(FAMILY, f, o, m, 0.3, 30, 25, 32, (N or 1024) // 2 + 1, frame_size=N or 1024, hop=512,
+                           out_name=name, window=w, device=dev, slot=slot)
+    return _common.cli_main(argv, USAGE, lambda i, o, m: train_auto(i, o, m, 0.3, 30, 25, 32, 513), run_one)  # separate_dsd.py:332
 
 
 if __name__ == "__main__":

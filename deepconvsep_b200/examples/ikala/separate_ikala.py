@@ -3,7 +3,6 @@
     python -m deepconvsep_b200.examples.ikala.separate_ikala -i <inputfile> -o <outputdir> -m <path_to_model.pkl>
 """
 import sys
-import getopt
 import numpy as np
 
 from ...models import load_model                       # noqa: F401
@@ -39,26 +38,12 @@ def train_auto(filein, outdir, model, scale_factor=0.3, time_context=30, overlap
 
 
 def main(argv):
-    try:
-        opts, args = getopt.getopt(argv, "hi:o:m:", ["ifile=", "odir=", "mfile="])
-    except getopt.GetoptError:
-        print(USAGE)
-        sys.exit(2)
-    inputfile = outdir = model = None
-    for opt, arg in opts:
-        if opt == '-h':
-            print(USAGE)
-            sys.exit()
-        elif opt in ("-i", "--ifile"):
-            inputfile = arg
-        elif opt in ("-o", "--odir"):
-            outdir = arg
-        elif opt in ("-m", "--mfile"):
-            model = arg
-    if inputfile is None or outdir is None or model is None:
-        print(USAGE)
-        sys.exit(2)
-    train_auto(inputfile, outdir, model, 0.3, 30, 20, 32, 513)      # separate_ikala.py:275
+    """`-i -o -m` as the reference script; extra long options: see _common.parse_cli."""
+    return _common.cli_main(
+        argv, USAGE,
+        lambda i, o, m: train_auto(i, o, m, 0.3, 30, 20, 32, 513),   # separate_ikala.py:275
+        lambda f, o, m, N, w, dev, slot, several: _common.run(FAMILY, f, o, m, 0.3, 30, 20, 32, (N or 1024) // 2 + 1, frame_size=N or 1024, hop=512,
+                                                     out_name=lambda fn, src: fn.replace(".wav", "-" + src + ".wav"), window=w, device=dev, slot=slot))
 
 
 if __name__ == "__main__":

@@ -56,10 +56,12 @@ def infer_arch(params, feat_size=None):
     """(arch, feat_size, time_context) from the parameter shapes (the .pkl carries no names)."""
     n = len(params)
     s0, s3, s6 = params[0].shape, params[3].shape, params[6].shape
+    # DSD nets: conv2 has kh2 = int(tc/2) taps and leaves h2 = tc - kh2 + 1 rows, fc.W has 50*h2 rows: tc = h2 + kh2 - 1
+    # (2*kh2 would be wrong for an odd time_context)
     if n == 15 and len(s0) == 4 and s0[0] == 50:
-        return "dsd", int(s0[3]), 2 * int(s3[2])
+        return "dsd", int(s0[3]), int(s6[0]) // 50 + int(s3[2]) - 1
     if n == 17 and len(s0) == 4 and s0[0] == 50 and s0[1] == 2:
-        return "dsd_ild", int(s0[3]), 2 * int(s3[2])
+        return "dsd_ild", int(s0[3]), int(s6[0]) // 50 + int(s3[2]) - 1
     cands = (513, 1025, 2049, 257, 129, 65) if feat_size is None else (feat_size,)
     if n == 13 and s0[0] == 30:
         for F in cands:

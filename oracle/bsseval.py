@@ -112,8 +112,11 @@ def bss_eval_sources(se, s, flen=FLEN):
             e_interf = p_all - s_true - e_spat
             e_artif = se_pad - s_true - e_spat - e_interf
             SDR[jest, jtrue], SIR[jest, jtrue], SAR[jest, jtrue] = source_crit(s_true, e_spat, e_interf, e_artif)
-    best, perm = -np.inf, None
-    for p in itertools.permutations(range(n)):
+    # perms(1:nsrc) enumerates in reverse lexicographic order, max() keeps the first maximum and returns
+    # index 1 when every mean is NaN / -Inf (bss_eval_sources.m:56-63)
+    cands = sorted(itertools.permutations(range(n)), reverse=True)
+    best, perm = -np.inf, cands[0]
+    for p in cands:
         m = np.mean([SIR[p[j], j] for j in range(n)])
         if m > best:
             best, perm = m, p

@@ -60,3 +60,55 @@ def test_bss_eval_rejects_host_tensors():
     from deepconvsep_b200 import evaluation
     with pytest.raises(ValueError):
         evaluation.bss_eval_sources(torch.zeros(2, 100), torch.zeros(2, 100))
+
+
+def _stereo_case(nsrc, L, seed):
+    rng = np.random.default_rng(seed)
+    s = np.stack([np.stack([np.convolve(rng.standard_normal(L + 40), rng.standard_normal(5 + 2 * k + c))[20:20 + L]
+                            for c in range(2)]) for k in range(nsrc)])                       # [nsrc, 2, L]
+    est = s + 0.3 * rng.standard_normal(s.shape) * s.std(axis=2, keepdims=True) + 0.2 * np.roll(s, 1, axis=0)
+    return s.astype(np.float32), est.astype(np.float32)
+
+
+def test_bss_eval_windowed_images_matches_oracle_on_device_lags():
+    """the variant DSD100 is scored with (evaluation/DSD100_eval_only.m:211-306: `bss_eval(ie, i, win, ove)`, stereo
+    images, 512-tap distortion filters, overlapping windows, estimate j against source j, SDR / ISR / SIR / SAR):
+    device lags + host algebra against the explicit decomposition of the oracle; the time split of the two
+    halves is written to gpurun_out/bsseval_r2.json"""
+    import json
+    import os
+    import time
+    from deepconvsep_b200 import evaluation
+    from deepconvsep_b200.engine import Context
+    nsrc, L, win, ove, flen = 3, 36000, 16000, 8000, 128
+    s32, e32 = _stereo_case(nsrc, L, 5)
+    ctx = Context(0)
+    se, sr = torch.tensor(e32, device="cuda"), torch.tensor(s32, device="cuda")
+    got = evaluation.bss_eval_windowed(se, sr, win, ove, flen=flen, ctx=ctx)
+    want = bsseval.bss_eval_windowed(e32.astype(np.float64), s32.astype(np.float64), win, ove, flen=flen)
+    assert got[0].shape == want[0].shape == (nsrc, len(bsseval.window_starts(L, win, ove))) and got[0].shape[1] >= 3
+    for name, g, w in zip(("SDR", "ISR", "SIR", "SAR"), got, want):
+        assert np.max(np.abs(g - w)) < 1e-6, (name, g, w)
+    # one window at the real filter length (512 taps, the reference's default): where does the time go?
+    nsrc2, L2 = 4, 30 * 44100
+    s2, e2 = _stereo_case(nsrc2, L2, 6)
+    se2, sr2 = torch.tensor(e2, device="cuda"), torch.tensor(s2, device="cuda")
+    kinds, idx = evaluation.image_pair_list(nsrc2, 2)
+    sig = {"ss": (sr2, sr2), "se": (sr2, se2), "ee": (se2, se2)}
+    pairs = [(sig[k][0][a // 2, a % 2], sig[k][1][b // 2, b % 2]) for k, a, b in kinds]
+    evaluation.xcorr_lags(ctx, pairs[:4], L2, 512)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    R = evaluation.xcorr_lags(ctx, pairs, L2, 512)
+    t_lags = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    r = evaluation.images_from_lags(R, idx, nsrc2, 2, 512)
+    t_host = time.perf_counter() - t0
+    assert all(np.isfinite(x).all() for x in r)
+    # algorithmic work of the lag kernel: every pair reads its two signals once per 4-lag group
+    rec = {"case": "bss_eval_images, 4 stereo sources, one 30 s window, 512 taps", "pairs": len(pairs),
+           "device_lags_s": t_lags, "host_gram_solve_s": t_host,
+           "lag_macs": len(pairs) * 1023 * float(L2), "lag_fp64_gflops": 2 * len(pairs) * 1023 * float(L2) / t_lags / 1e9}
+    os.makedirs(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out"), exist_ok=True)
+    with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "bsseval_r2.json"), "w") as f:
+        json.dump(rec, f)

@@ -117,3 +117,30 @@ def test_dataset_runner_dsd100(tmp_path):
             assert np.mean(d > 1) < 2e-3
     # sharding: two ranks split the two songs
     assert len(runner.list_jobs("dsd", str(db), str(out))) == 2
+
+
+def test_cli_long_options_directory_of_clips(tmp_path):
+    """--frame-size / --window / --devices / --batch-clips with -i <directory>: two clips in flight on
+    device 0, every stem equal to what the plain `-i file` call writes."""
+    from deepconvsep_b200 import save_model
+    from deepconvsep_b200.examples.dsd100 import separate_dsd
+    params = nets.make_synthetic_params("dsd", 513, seed=21)
+    pkl = str(tmp_path / "model.pkl")
+    save_model(pkl, params)
+    indir, out1, out2 = tmp_path / "in", tmp_path / "out1", tmp_path / "out2"
+    for d in (indir, out1, out2):
+        os.makedirs(str(d))
+    names = []
+    for k, secs in enumerate((1.5, 2.2, 1.1)):
+        mix, _ = pipeline.synth_mixture(secs, 40 + k)
+        pcm = np.stack([np.round(mix * 30000), np.round(mix * 28000)], axis=1).astype(np.int16)
+        names.append("clip%d.wav" % k)
+        scipy.io.wavfile.write(str(indir / names[-1]), 44100, pcm)
+    separate_dsd.main(["-i", str(indir), "-o", str(out2), "-m", pkl, "--frame-size", "1024", "--window", "hanning",
+                       "--devices", "0", "--batch-clips", "2"])
+    for n in names:
+        separate_dsd.main(["-i", str(indir / n), "-o", str(out1), "-m", pkl])
+        for src in ["vocals", "bass", "drums", "other"]:
+            _, a = scipy.io.wavfile.read(str(out1 / (src + ".wav")))
+            _, b = scipy.io.wavfile.read(str(out2 / n.replace(".wav", "_" + src + ".wav")))
+            assert np.array_equal(a, b), (n, src)
