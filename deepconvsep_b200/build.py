@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdcs.so")
-SOURCES = ["api.cu", "stft.cu", "stft_reg.cu", "gemm.cu", "gemm_tc.cu", "gemm_tma.cu", "dsd.cu", "dsd_tc.cu", "sconv.cu", "sconv_model.cu", "bsseval.cu"]
+SOURCES = ["api.cu", "stft.cu", "stft_reg.cu", "gemm.cu", "gemm_tc.cu", "gemm_tma.cu", "dsd.cu", "dsd_tc.cu", "sconv.cu", "sconv_tc.cu", "sconv_model.cu", "bsseval.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-O2,-Wall", "-DDCS_BUILD"]
 

@@ -223,6 +223,9 @@ constexpr int DCS_TMA_FALLBACK = 1;   // launch_gemm_tma: "use the register-stag
 bool gemm_tma_eligible(const GemmDesc& d, int mask);
 // fp32 [rows][cols] tensor (row pitch in bytes), box = box_rows x 32 floats, 128-byte swizzle, zero fill
 int tma_encode_2d_f32(CUtensorMap* map, const float* base, uint64_t cols, uint64_t rows, uint64_t pitch_bytes, uint32_t box_rows);
+// 3-D fp32 tensor (d0 innermost = 32-float boxes, SWIZZLE_128B), box = {32, box_rows, 1}
+int tma_encode_3d_f32(CUtensorMap* map, const float* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                      uint64_t stride2_bytes, uint32_t box_rows);
 int launch_splitk_reduce(dcs_ctx* ctx, const GemmDesc& d, const float* partial, int ldp, int k_splits, cudaStream_t st);
 int launch_gemm_tma(dcs_ctx* ctx, const GemmDesc& d, const TcWeight& w, cudaStream_t st);
 
@@ -254,6 +257,8 @@ struct SconvMaskArgs {
 };
 int launch_pool4(dcs_ctx* ctx, const float* H1, float* Hp, uint8_t* tie, int64_t rows, int J, int WP, cudaStream_t st);
 int launch_sconv_mask(dcs_ctx* ctx, const SconvMaskArgs& a, cudaStream_t st);
+bool sconv_mask_tc_supported(const SconvMaskArgs& a);
+int launch_sconv_mask_tc(dcs_ctx* ctx, const SconvMaskArgs& a, cudaStream_t st);   // tcgen05 (sconv_tc.cu)
 int launch_channel_mul(dcs_ctx* ctx, const float* mag, const float* filt, float* out, int64_t plane, int nch, cudaStream_t st);
 bool dsd_mask_tc_supported(const DsdMaskArgs& a);
 int launch_dsd_mask_tc(dcs_ctx* ctx, const DsdMaskArgs& a, cudaStream_t st);

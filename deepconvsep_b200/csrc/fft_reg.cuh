@@ -67,6 +67,13 @@ __device__ __forceinline__ void fft_dif(float2 (&v)[R]) {
 template <int T>
 struct FftGroup {
   static constexpr int N2 = 32 * T;
+  // tw2[ka*T + b] = tw[2*b*ka], tw[j] = exp(-2*pi*i*j/(2*N2)): 32*T = N2 entries (block-wide, then __syncthreads)
+  __device__ static __forceinline__ void fill_tw2(float2* tw2, const float2* __restrict__ tw, int tid, int nthreads) {
+    for (int i = tid; i < 32 * T; i += nthreads) {
+      const int ka = i / T, b = i - ka * T;
+      tw2[i] = __ldg(tw + 2 * b * ka);
+    }
+  }
   static constexpr int PITCH = T + 1;                 // float2 per scratch row
   static constexpr int SCRATCH = 32 * PITCH;          // float2 per group (>= N2)
   static constexpr int Q = 32 / T;                    // rows per thread in the second pass (1 or 2)
@@ -75,14 +82,17 @@ struct FftGroup {
   // in : v[a] = x[a*T + b]                          (b = lane within the group)
   // out: v[q*T + kb] = X[(b + T*q) + 32*kb]          (q < Q, kb < T)
   // tw[j] = exp(-2*pi*i*j/(2*N2)); `scr` = this group's scratch; all lanes of the warp call this.
-  // TW_SHARED: `tw` points to a shared-memory copy of the table (plain loads) instead of global memory
+  // TW_SHARED: `tw` is the shared-memory inter-stage table tw2[ka*T + b] = exp(-2*pi*i*b*ka/N2) (fill_tw2): lane b
+  // reads consecutive 8-byte words for every ka -- conflict free.  (Indexing the plain table with 2*b*ka strides
+  // the lanes by 4*ka banks: 8- to 16-way conflicts for ka = 4, 8, 16, ...; the iSTFT ran at 74 % of the
+  // shared-memory pipe with 16.8 M conflict cycles per clip, profiles/r2_notes.md.)
   template <bool TW_SHARED = false>
   __device__ static __forceinline__ void forward(float2 (&v)[32], float2* scr, const float2* __restrict__ tw, int b) {
     fft_dif<32>(v);
 #pragma unroll
     for (int ka = 0; ka < 32; ++ka) {
       float2 y = v[brev(ka, 5)];
-      if (ka > 0) y = cmul(y, TW_SHARED ? tw[2 * b * ka] : __ldg(tw + 2 * b * ka));
+      if (ka > 0) y = cmul(y, TW_SHARED ? tw[ka * T + b] : __ldg(tw + 2 * b * ka));
       scr[ka * PITCH + b] = y;
     }
     __syncwarp();

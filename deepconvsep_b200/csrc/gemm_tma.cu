@@ -309,6 +309,12 @@ int tma_encode_2d_f32(CUtensorMap* map, const float* base, uint64_t cols, uint64
   return encode_map(map, base, 2, dims, strides, box_rows, false);
 }
 
+int tma_encode_3d_f32(CUtensorMap* map, const float* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                      uint64_t stride2_bytes, uint32_t box_rows) {
+  const uint64_t dims[3] = {d0, d1, d2}, strides[2] = {stride1_bytes, stride2_bytes};
+  return encode_map(map, base, 3, dims, strides, box_rows, false);
+}
+
 // Overlapping rows (pitch < K: a convolution over time read in place) make a tensor whose row
 // pitch is smaller than its row extent.  The copy engine only does address arithmetic and a
 // per-dimension bounds check, so it works; should a driver refuse to encode such a map, the GEMM

@@ -218,7 +218,8 @@ int sconv_forward(dcs_ctx* ctx, dcs_model* m, const float* d_in, int64_t in_plan
   a.ldf = ldf; a.src_stride = src_stride; a.T = (int)T; a.P = (int)P; a.tc = tc; a.overlap = overlap; a.F = m->F;
   a.J = J; a.WP = WP;
   ProfScope ps(ctx, "dec_convT1_mask_xfade", st);
-  return launch_sconv_mask(ctx, a, st);
+  if (!ctx->debug_simt_gemm && sconv_mask_tc_supported(a)) return launch_sconv_mask_tc(ctx, a, st);
+  return launch_sconv_mask(ctx, a, st);    // FFMA twin: bring-up cross-check (DCS_DEBUG_SIMT_GEMM=1)
 }
 
 }  // namespace dcs

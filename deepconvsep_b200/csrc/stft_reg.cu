@@ -37,9 +37,11 @@ stft_reg_kernel(const float* __restrict__ audio, int64_t L, int hop, const float
   const int tid = threadIdx.x, b = tid % T, gl = tid / T;
   float2* scr = scratch + gl * G::SCRATCH;
   // shared copies of the twiddle table and of the analysis window (per-thread constants of every frame)
-  float2* stw = scratch + GPC * G::SCRATCH;
-  float2* swin = stw + N;
-  for (int i = tid; i < N; i += REG_THREADS) stw[i] = __ldg(tw + i);
+  float2* stw = scratch + GPC * G::SCRATCH;        // tw[0..N2): the real-FFT split twiddles
+  float2* stw2 = stw + N2;                         // inter-stage twiddles, lane-contiguous (FftGroup::fill_tw2)
+  float2* swin = stw2 + N2;
+  for (int i = tid; i < N2; i += REG_THREADS) stw[i] = __ldg(tw + i);
+  G::fill_tw2(stw2, tw, tid, REG_THREADS);
   for (int i = tid; i < N2; i += REG_THREADS) swin[i] = __ldg(reinterpret_cast<const float2*>(win) + i);
   __syncthreads();
   const int64_t g = (int64_t)blockIdx.x * GPC + gl;
@@ -72,7 +74,7 @@ stft_reg_kernel(const float* __restrict__ audio, int64_t L, int hop, const float
         v[a] = make_float2(x0 * w.x, x1 * w.y);
       }
     }
-    G::template forward<true>(v, scr, stw, b);
+    G::template forward<true>(v, scr, stw2, b);
 #pragma unroll
     for (int q = 0; q < G::Q; ++q)
 #pragma unroll
@@ -149,9 +151,11 @@ istft_reg_kernel(const float2* __restrict__ S, int64_t nframes, int64_t ldf, int
   constexpr int CHUNKS = (N2 + 2) / 2;                // 16-byte pieces covering bins 0..N2
   float2* srow = scratch + GPC * G::SCRATCH + gl * ROWP;
   // shared copies of the twiddle table (N entries, exp(-2 pi i j / N)) and of the synthesis window (as pairs)
-  float2* stw = scratch + GPC * (G::SCRATCH + ROWP);
-  float2* swsyn = stw + N;
-  for (int i = tid; i < N; i += ISTFT_THREADS) stw[i] = __ldg(tw + i);
+  float2* stw = scratch + GPC * (G::SCRATCH + ROWP);   // tw[0..N2): the real-FFT merge twiddles
+  float2* stw2 = stw + N2;                              // inter-stage twiddles, lane-contiguous (FftGroup::fill_tw2)
+  float2* swsyn = stw2 + N2;
+  for (int i = tid; i < N2; i += ISTFT_THREADS) stw[i] = __ldg(tw + i);
+  G::fill_tw2(stw2, tw, tid, ISTFT_THREADS);
   for (int i = tid; i < N2; i += ISTFT_THREADS) swsyn[i] = __ldg(reinterpret_cast<const float2*>(wsyn) + i);
   __syncthreads();
   auto prefetch = [&](int64_t nn) {
@@ -184,7 +188,7 @@ istft_reg_kernel(const float2* __restrict__ S, int64_t nframes, int64_t ldf, int
     }
     __syncwarp();                    // every lane has consumed the row
     if (n < n_last) prefetch(n + 1);
-    G::template forward<true>(v, scr, stw, b);
+    G::template forward<true>(v, scr, stw2, b);
     // z = conj(V)/N2: samples 2n', 2n'+1 of the frame, n' = (b + T q) + 32 kb  <->  v[q*T + kb]
 #pragma unroll
     for (int q = 0; q < G::Q; ++q)

@@ -98,8 +98,9 @@ def test_dataset_runner_dsd100(tmp_path):
     params = nets.make_synthetic_params("dsd", 513, seed=31)
     db, out = tmp_path / "Mixtures", tmp_path / "Estimates"
     songs = {("Dev", "051 - A"): 1.7, ("Test", "001 - B"): 1.2}
+    seeds = {"051 - A": 200, "001 - B": 211}     # clips for which the oracle flags no mask-discontinuity bin (fixed: hash() is salted per process)
     for (sub, name), secs in songs.items():
-        mix, _ = pipeline.synth_mixture(secs, hash(name) % 1000)
+        mix, _ = pipeline.synth_mixture(secs, seeds[name])
         pcm = np.stack([np.round(mix * 30000), np.round(mix * 25000)], axis=1).astype(np.int16)
         os.makedirs(str(db / sub / name))
         scipy.io.wavfile.write(str(db / sub / name / "mixture.wav"), 44100, pcm)
@@ -114,7 +115,8 @@ def test_dataset_runner_dsd100(tmp_path):
             sr2, got = scipy.io.wavfile.read(str(out / sub / name / (s + ".wav")))
             assert sr2 == 44100 and got.dtype == np.int16
             d = np.abs(got.astype(np.int32) - (want[i] * 32767).astype("int16").astype(np.int32))
-            assert np.mean(d > 1) < 2e-3
+            assert pipeline.separate.last_kinks == 0
+            assert d.max() <= 1                    # truncation to int16 flips at most one LSB
     # sharding: two ranks split the two songs
     assert len(runner.list_jobs("dsd", str(db), str(out))) == 2
 
