@@ -118,6 +118,12 @@ int dcs_create(int device, dcs_ctx** out) {
   c->tma_wide = tn && tn[0] == '1';
   const char* tk = getenv("DCS_DEBUG_TMA_MASK");
   if (tk && tk[0] >= '0' && tk[0] <= '9') c->tma_mask = atoi(tk);
+  const char* tp = getenv("DCS_DEBUG_TMA_PREFETCH");
+  if (tp && tp[0] >= '0' && tp[0] <= '9') c->tma_prefetch = atoi(tp);
+  const char* tr = getenv("DCS_DEBUG_TMA_PROBE");
+  if (tr && tr[0] >= '0' && tr[0] <= '9') c->tma_probe = atoi(tr);
+  const char* tq = getenv("DCS_DEBUG_TMA_PERSIST");
+  if (tq && tq[0] >= '0' && tq[0] <= '9') c->tma_persist = atoi(tq);
   const char* ty = getenv("DCS_DEBUG_TMA_SYNC");
   c->tma_sync = ty && ty[0] == '1';
   *out = c;

@@ -74,6 +74,9 @@ struct dcs_ctx {
   bool tma_wide = false; // DCS_DEBUG_TMA_WIDE: 128-wide tiles (one CTA per SM) for N > 64
   int tma_mask = 31;     // DCS_DEBUG_TMA_MASK: which operand views may take the TMA kernel
   bool tma_sync = false; // DCS_DEBUG_TMA_SYNC: synchronise after each TMA GEMM
+  int tma_prefetch = 0;  // DCS_DEBUG_TMA_PREFETCH: activation boxes prefetched into L2 ahead of the stage ring (measured: no gain)
+  int tma_probe = 0;     // DCS_DEBUG_TMA_PROBE: timing experiments on the TMA GEMM (results are wrong)
+  int tma_persist = 8;   // DCS_DEBUG_TMA_PERSIST: persistent GEMM for short-K tiles when tiles >= this x SMs (0 = never)
   bool debug_smem_fft = false;
   std::vector<dcs_prof_rec> prof;
   // workspace of one in-flight pipeline

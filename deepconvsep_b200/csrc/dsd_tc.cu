@@ -120,7 +120,7 @@ dsd_mask_tc_kernel(const DsdMaskArgs a, const __grid_constant__ CUtensorMap tmG,
 
   if (warp == MT_TMA_WARP) {
     // ------------------------------------------------------------------ copy engine
-    if (lane == 0) {
+    if (elect_one()) {
       for (int g = g_begin; g < g_end; ++g) {
         const int it = g - g_begin, s = it & 1;
         mbar_wait(&empty_b[s], ((it >> 1) & 1) ^ 1);
@@ -150,7 +150,7 @@ dsd_mask_tc_kernel(const DsdMaskArgs a, const __grid_constant__ CUtensorMap tmG,
     }
   } else if (warp == MT_EPI_WARPS) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = make_idesc_tf32(MT_BINS, MT_COLS);
       const uint32_t a_hi = smem_u32(sA), a_lo = a_hi + 2 * MT_A_SUB;
       for (int g = g_begin; g < g_end; ++g) {

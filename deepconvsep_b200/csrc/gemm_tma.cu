@@ -65,6 +65,9 @@ struct TmaGemmArgs {
   int acc_mode;
   int rewrite_hi;     // store trunc_tf32(x) over the raw tile (bring-up cross-check)
   int cvec;           // C rows allow 16-byte stores
+  int probe;          // DCS_DEBUG_TMA_PROBE (timing experiments, wrong results): 1 no low-plane work, 2 no MMAs, 4 no B loads,
+                      // 8 no A loads, 16 only the main product (1 of 3 MMAs per k-step)
+  int prefetch;       // A boxes prefetched into L2 ahead of the stage ring (DCS_DEBUG_TMA_PREFETCH, default 6; 0 = off)
   int k_splits;       // > 1: blockIdx.z owns a slice of the k-blocks and stores raw partial sums
   int ldp;            // row pitch of the partial-sum workspace
   float* partial;
@@ -130,55 +133,74 @@ gemm_tma_kernel(const GemmDesc d, const __grid_constant__ CUtensorMap tmA, const
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == TM_TMA_WARP) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ---------------------------------------------------------------- copy engine
+      // the activation boxes of the next PF k-blocks are prefetched into L2 while the stage ring (2 stages x 2 CTAs)
+      // is busy: a tile's first touch of HBM is then off the TMA -> low plane -> MMA -> commit chain
+      const int PF = g.prefetch;
+      auto prefetch_a = [&](int kb) {
+        if (g.conv) {
+          const int q = (kb_lo + kb) / g.kw, w = (kb_lo + kb) - q * g.kw;
+          tma_prefetch_4d(&tmA, 0, r0 + w, u + q, kd);
+        } else {
+          tma_prefetch_2d(&tmA, u * g.col_per_u + (kb_lo + kb) * KSTAGE, r0);
+        }
+      };
+      for (int kb = STAGES; kb < min(num_kb, STAGES + PF); ++kb) prefetch_a(kb);
+      int cq = kb_lo / g.kw, cw = kb_lo - cq * g.kw;     // running (time tap, position tap) of the conv view
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % STAGES;
+        if (PF > 0 && kb + STAGES + PF < num_kb) prefetch_a(kb + STAGES + PF);
         mbar_wait(&empty[s], ((kb / STAGES) & 1) ^ 1);
         uint8_t* st = smem + s * SM::STAGE_BYTES;
         const int k0 = (kb_lo + kb) * KSTAGE;
-        mbar_arrive_expect_tx(&full[s], a_tx + 2 * SM::B_BYTES);
-        if (g.conv) {
-          const int q = (kb_lo + kb) / g.kw, w = (kb_lo + kb) - q * g.kw;
-          tma_load_4d(st, &tmA, &full[s], 0, r0 + w, u + q, kd);
-        } else {
-          tma_load_2d(st, &tmA, &full[s], u * g.col_per_u + k0, r0);
+        const bool ldA = !(g.probe & 8), ldB = !(g.probe & 4);
+        mbar_arrive_expect_tx(&full[s], (ldA ? a_tx : 0) + (ldB ? 2 * SM::B_BYTES : 0));
+        if (ldA) {
+          if (g.conv) {
+            tma_load_4d(st, &tmA, &full[s], 0, r0 + cw, u + cq, kd);
+            if (++cw == g.kw) { cw = 0; ++cq; }
+          } else {
+            tma_load_2d(st, &tmA, &full[s], u * g.col_per_u + k0, r0);
+          }
         }
-        tma_load_2d(st + 2 * SM::A_BYTES, &tmB, &full[s], k0, n0);
-        tma_load_2d(st + 2 * SM::A_BYTES + SM::B_BYTES, &tmB, &full[s], k0, g.Np + n0);
+        if (ldB) {
+          tma_load_2d(st + 2 * SM::A_BYTES, &tmB, &full[s], k0, n0);
+          tma_load_2d(st + 2 * SM::A_BYTES + SM::B_BYTES, &tmB, &full[s], k0, g.Np + n0);
+        }
       }
     }
   } else if (warp == TM_MMA_WARP) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ---------------------------------------------------------------- MMA issuer
+      // one thread, ~12 MMAs per k-block: everything the loop needs per MMA is one 32-bit add (descriptor low word)
+      // -- no divisions, no 64-bit descriptor rebuilds; the accumulator rotation is a counter
       constexpr uint32_t idesc = make_idesc_tf32(TM_BM, BN);
+      constexpr uint32_t ST_D = SM::STAGE_BYTES >> 4, A_D = SM::A_BYTES >> 4, B_D = SM::B_BYTES >> 4;
+      const uint32_t lo0 = desc_lo(smem_u32(smem));
+      const uint32_t t_corr = tmem_base + corr_acc * BN;
+      const bool p_ab = !(g.probe & (2 | 16)), p_main = !(g.probe & 2);
+      int ma = 0, ks = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t par = (kb / STAGES) & 1;
         mbar_wait(&full[s], par);
         fence_after_sync();
-        const uint32_t a_hi = smem_u32(smem + s * SM::STAGE_BYTES);
-        const uint32_t a_lo = a_hi + SM::A_BYTES;
-        const uint32_t b_hi = a_hi + 2 * SM::A_BYTES;
-        const uint32_t b_lo = b_hi + SM::B_BYTES;
+        const uint32_t a_hi = lo0 + s * ST_D, a_lo = a_hi + A_D, b_hi = a_hi + 2 * A_D, b_lo = b_hi + B_D;
         // the two products that only need what the copy engine delivered go first; the one with
         // the derived low plane of A follows when the writers are done (off the critical path)
 #pragma unroll
-        for (int j = 0; j < KSTAGE / 8; ++j) {
-          const uint64_t dah = make_desc(a_hi + KSTEP_BYTES * j);
-          const uint64_t dbh = make_desc(b_hi + KSTEP_BYTES * j), dbl = make_desc(b_lo + KSTEP_BYTES * j);
-          const int ks = kb * (KSTAGE / 8) + j;
-          const int ma = ks % n_main;
-          umma_tf32(tmem_base + corr_acc * BN, dah, dbl, idesc, ks != 0);
-          umma_tf32(tmem_base + ma * BN, dah, dbh, idesc, corr_acc == 0 ? 1 : (ks >= n_main));
+        for (int j = 0; j < KSTAGE / 8; ++j, ++ks) {
+          if (p_ab) umma_tf32(t_corr, desc_of(a_hi + KSTEP_DESC * j), desc_of(b_lo + KSTEP_DESC * j), idesc, ks != 0);
+          if (p_main) umma_tf32(tmem_base + ma * BN, desc_of(a_hi + KSTEP_DESC * j), desc_of(b_hi + KSTEP_DESC * j), idesc,
+                                corr_acc == 0 ? 1 : (ks >= n_main));
+          ma = ma + 1 == n_main ? 0 : ma + 1;
         }
         mbar_wait(&split[s], par);
         fence_after_sync();
 #pragma unroll
-        for (int j = 0; j < KSTAGE / 8; ++j) {
-          const uint64_t dal = make_desc(a_lo + KSTEP_BYTES * j), dbh = make_desc(b_hi + KSTEP_BYTES * j);
-          umma_tf32(tmem_base + corr_acc * BN, dal, dbh, idesc, 1);
-        }
+        for (int j = 0; j < KSTAGE / 8; ++j)
+          if (p_ab) umma_tf32(t_corr, desc_of(a_lo + KSTEP_DESC * j), desc_of(b_hi + KSTEP_DESC * j), idesc, 1);
         umma_commit(&empty[s]);
       }
       umma_commit(tmem_full);
@@ -192,6 +214,7 @@ gemm_tma_kernel(const GemmDesc d, const __grid_constant__ CUtensorMap tmA, const
       float4* lo = reinterpret_cast<float4*>(smem + s * SM::STAGE_BYTES + SM::A_BYTES);
       constexpr int CHUNKS = SM::A_BYTES / 16 / (TM_SPLIT_WARPS * 32);   // 8 per thread
       float4 x[CHUNKS];
+      if (g.probe & 1) { mbar_arrive(&split[s]); continue; }
 #pragma unroll
       for (int i = 0; i < CHUNKS; ++i) x[i] = raw[i * (TM_SPLIT_WARPS * 32) + tid];
 #pragma unroll
@@ -264,6 +287,243 @@ gemm_tma_kernel(const GemmDesc d, const __grid_constant__ CUtensorMap tmA, const
   if (warp == TM_MMA_WARP) {
     fence_after_sync();
     tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---- persistent variant ------------------------------------------------------------------------
+// Same tiles, same operand views, same accumulation plan -- but ONE CTA per SM walks a strided list of tiles with
+//   * a stage ring that runs on across tile boundaries (no fill / drain per tile),
+//   * two TMEM accumulator sets, so the epilogue of tile i runs under the main loop of tile i+1,
+//   * dedicated epilogue warps (the low-plane writers never leave the ring).
+// The one-tile-per-CTA kernel above pays launch + barrier init + TMEM alloc + pipeline fill + drain + epilogue for
+// every 128-row tile; when a tile is only a handful of k-blocks (the transposed convolutions after tap clipping:
+// 7 of 20 taps for Bach10, 13 of 25 for DSD100) that skeleton IS the run time (profiles/r2_notes.md: 245 760
+// tiles x ~10 us / 296 resident CTAs = 8.3 of the 9.4 ms of Bach10's InverseLayer(conv2)).
+//   warps 0-3 epilogue | warp 4 MMA issue + TMEM alloc | warp 5 copy engine | warps 6-9 low plane
+constexpr int TP_THREADS = 10 * 32;
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TP_THREADS, 1)
+gemm_tma_persist_kernel(const GemmDesc d, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                        const TmaGemmArgs g, int tiles_x, int tiles_y) {
+  using SM = TmSmem<BN, STAGES>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFF);
+  uint64_t* split = full + STAGES;
+  uint64_t* empty = split + STAGES;
+  uint64_t* tmem_full = empty + STAGES;      // [2]
+  uint64_t* tmem_empty = tmem_full + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_kdg = (g.n_kd + g.kdb - 1) / g.kdb;
+  const int per_u = g.tiles_pos * n_kdg;
+  const int64_t total_tiles = (int64_t)tiles_x * tiles_y;
+  const uint32_t a_tx = (uint32_t)(g.pb * g.tb * g.kdb) * ROW_BYTES;
+  const int n_main = g.acc_mode == 2 ? 3 : 1;
+  const int corr_acc = g.acc_mode == 0 ? 0 : n_main;
+  constexpr uint32_t SET_COLS = 4 * BN;
+
+  // tile id -> (first output time / plane / position of the tile, first output column, k-block range)
+  struct Tile { int u, kd, r0, n0, kb_lo, num_kb; };
+  auto decode = [&](int64_t t) {
+    Tile x;
+    const int bx = (int)(t / tiles_y);
+    x.n0 = (int)(t - (int64_t)bx * tiles_y) * BN;
+    const int ug = bx / per_u;
+    const int kdg = (bx - ug * per_u) / g.tiles_pos;
+    x.u = ug * g.tb;
+    x.kd = kdg * g.kdb;
+    x.r0 = (bx - ug * per_u - kdg * g.tiles_pos) * g.pb;
+    int kb_lo = 0, kb_hi = (d.K + KSTAGE - 1) / KSTAGE;
+    if (d.kc_rows > 0) {
+      const int q_lo = max(0, d.kc_pad - x.u), q_hi = min(d.kc_taps - 1, d.kc_pad + d.kc_n - 1 - x.u);
+      kb_lo = (d.kc_unit * q_lo) / KSTAGE;
+      kb_hi = min(kb_hi, (d.kc_unit * (q_hi + 1) + KSTAGE - 1) / KSTAGE);
+      if (kb_hi <= kb_lo) kb_hi = kb_lo + 1;
+    }
+    x.kb_lo = kb_lo;
+    x.num_kb = kb_hi - kb_lo;
+    return x;
+  };
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&split[s], TM_SPLIT_WARPS * 32);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 5 && lane == 0) {
+    prefetch_tensormap(&tmA);
+    prefetch_tensormap(&tmB);
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, 2 * SET_COLS);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 5) {
+    if (elect_one()) {
+      // ---------------------------------------------------------------- copy engine
+      int it = 0;
+      for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const Tile x = decode(t);
+        for (int kb = 0; kb < x.num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+          uint8_t* st = smem + s * SM::STAGE_BYTES;
+          const int k0 = (x.kb_lo + kb) * KSTAGE;
+          mbar_arrive_expect_tx(&full[s], a_tx + 2 * SM::B_BYTES);
+          if (g.conv) {
+            const int q = (x.kb_lo + kb) / g.kw, w = (x.kb_lo + kb) - q * g.kw;
+            tma_load_4d(st, &tmA, &full[s], 0, x.r0 + w, x.u + q, x.kd);
+          } else {
+            tma_load_2d(st, &tmA, &full[s], x.u * g.col_per_u + k0, x.r0);
+          }
+          tma_load_2d(st + 2 * SM::A_BYTES, &tmB, &full[s], k0, x.n0);
+          tma_load_2d(st + 2 * SM::A_BYTES + SM::B_BYTES, &tmB, &full[s], k0, g.Np + x.n0);
+        }
+      }
+    }
+  } else if (warp == 4) {
+    if (elect_one()) {
+      // ---------------------------------------------------------------- MMA issuer
+      constexpr uint32_t idesc = make_idesc_tf32(TM_BM, BN);
+      constexpr uint32_t ST_D = SM::STAGE_BYTES >> 4, A_D = SM::A_BYTES >> 4, B_D = SM::B_BYTES >> 4;
+      const uint32_t lo0 = desc_lo(smem_u32(smem));
+      int it = 0, ti = 0;
+      for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+        const Tile x = decode(t);
+        const int set = ti & 1;
+        const uint32_t acc = tmem_base + set * SET_COLS;
+        mbar_wait(&tmem_empty[set], ((ti >> 1) & 1) ^ 1);
+        fence_after_sync();
+        int ma = 0, ks = 0;
+        const uint32_t t_corr = acc + corr_acc * BN;
+        for (int kb = 0; kb < x.num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t par = (it / STAGES) & 1;
+          mbar_wait(&full[s], par);
+          fence_after_sync();
+          const uint32_t a_hi = lo0 + s * ST_D, a_lo = a_hi + A_D, b_hi = a_hi + 2 * A_D, b_lo = b_hi + B_D;
+#pragma unroll
+          for (int j = 0; j < KSTAGE / 8; ++j, ++ks) {
+            umma_tf32(t_corr, desc_of(a_hi + KSTEP_DESC * j), desc_of(b_lo + KSTEP_DESC * j), idesc, ks != 0);
+            umma_tf32(acc + ma * BN, desc_of(a_hi + KSTEP_DESC * j), desc_of(b_hi + KSTEP_DESC * j), idesc,
+                      corr_acc == 0 ? 1 : (ks >= n_main));
+            ma = ma + 1 == n_main ? 0 : ma + 1;
+          }
+          mbar_wait(&split[s], par);
+          fence_after_sync();
+#pragma unroll
+          for (int j = 0; j < KSTAGE / 8; ++j)
+            umma_tf32(t_corr, desc_of(a_lo + KSTEP_DESC * j), desc_of(b_hi + KSTEP_DESC * j), idesc, 1);
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&tmem_full[set]);
+      }
+    }
+  } else if (warp > 5) {
+    // ------------------------------------------------------------------ low-plane writers
+    const int pt = tid - 6 * 32;
+    int it = 0;
+    for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const Tile x = decode(t);
+      for (int kb = 0; kb < x.num_kb; ++kb, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(&full[s], (it / STAGES) & 1);
+        float4* raw = reinterpret_cast<float4*>(smem + s * SM::STAGE_BYTES);
+        float4* lo = reinterpret_cast<float4*>(smem + s * SM::STAGE_BYTES + SM::A_BYTES);
+        constexpr int CHUNKS = SM::A_BYTES / 16 / (TM_SPLIT_WARPS * 32);   // 8 per thread
+        float4 v[CHUNKS];
+#pragma unroll
+        for (int i = 0; i < CHUNKS; ++i) v[i] = raw[i * (TM_SPLIT_WARPS * 32) + pt];
+#pragma unroll
+        for (int i = 0; i < CHUNKS; ++i) {
+          float4 h, l;
+          split4(v[i], h, l);
+          lo[i * (TM_SPLIT_WARPS * 32) + pt] = l;
+        }
+        fence_proxy_async();
+        mbar_arrive(&split[s]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (thread = tile row = TMEM lane)
+    int ti = 0;
+    for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+      const Tile x = decode(t);
+      const int set = ti & 1;
+      const int n_main_used = min(n_main, x.num_kb * (KSTAGE / 8));
+      const int pos = x.r0 + tid % g.pb, t2 = tid / g.pb, tl = t2 % g.tb, kdl = t2 / g.tb;
+      const int64_t m64 = (int64_t)(x.u + tl) * g.m_inner + (int64_t)(x.kd + kdl) * g.n_pos + pos;
+      const bool m_ok = kdl < g.kdb && x.kd + kdl < g.n_kd && x.u + tl < g.n_u && pos < g.n_pos && m64 < d.M;
+      const int m = m_ok ? (int)m64 : 0;
+      const int64_t roff = gemm_c_row_offset(d, m);
+      const bool st_ok = m_ok && roff >= 0;
+      mbar_wait_relaxed(&tmem_full[set], (ti >> 1) & 1);
+      fence_after_sync();
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + set * SET_COLS;
+      const int n0 = x.n0;
+#pragma unroll 1
+      for (int j = 0; j < BN / 16; ++j) {
+        const bool live = n0 + 16 * j < d.N;  // warp-uniform
+        float v[16];
+        if (live) {
+          tmem_ld16(taddr + 16 * j, v);
+          for (int a = 1; a < n_main_used; ++a) {
+            float w[16];
+            tmem_ld16(taddr + a * BN + 16 * j, w);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += w[i];
+          }
+          if (corr_acc) {
+            float w[16];
+            tmem_ld16(taddr + corr_acc * BN + 16 * j, w);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += w[i];
+          }
+        }
+        if (j == BN / 16 - 1) {   // every column of this set has been read: the MMA warp may start tile i+2 in it
+          fence_before_sync();
+          mbar_arrive(&tmem_empty[set]);
+        }
+        if (live && st_ok) {
+#pragma unroll
+          for (int i4 = 0; i4 < 4; ++i4) {
+            const int n = n0 + 16 * j + 4 * i4;
+            float e4[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              e4[e] = v[4 * i4 + e];
+              if (d.bias && n + e < d.N) e4[e] += __ldg(d.bias + n + e);
+              if (d.relu) e4[e] = fmaxf(e4[e], 0.f);
+            }
+            if (g.cvec && n + 4 <= d.N) {
+              *reinterpret_cast<float4*>(d.C + roff + (int64_t)(n / d.n_seg) * d.n_ss + (n % d.n_seg)) = make_float4(e4[0], e4[1], e4[2], e4[3]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (n + e < d.N) d.C[roff + (int64_t)((n + e) / d.n_seg) * d.n_ss + ((n + e) % d.n_seg)] = e4[e];
+            }
+          }
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 4) {
+    fence_after_sync();
+    tmem_dealloc(tmem_base, 2 * SET_COLS);
   }
 }
 
@@ -434,6 +694,8 @@ static int launch_tma(dcs_ctx* ctx, const GemmDesc& d, const TcWeight& w, cudaSt
   g.Np = w.Np;
   g.acc_mode = ctx->tc_acc_mode;
   g.rewrite_hi = ctx->tma_mode == 2;
+  g.prefetch = ctx->tma_prefetch;
+  g.probe = ctx->tma_probe;
   g.cvec = ((uintptr_t)d.C % 16 == 0) && d.c_so % 4 == 0 && d.c_si % 4 == 0 && d.c_s2 % 4 == 0 && d.c_col0 % 4 == 0 &&
            (d.n_seg >= d.N || (d.n_seg % 4 == 0 && d.n_ss % 4 == 0));
   alignas(64) CUtensorMap tmA;
@@ -467,8 +729,29 @@ static int launch_tma(dcs_ctx* ctx, const GemmDesc& d, const TcWeight& w, cudaSt
     DCS_TRY(ctx->net[8].ensure((size_t)splits * d.M * g.ldp * sizeof(float), st));
     g.partial = ctx->net[8].as<float>();
   }
-  dim3 grid((unsigned)gx, (unsigned)ceil_div64(d.N, BN), (unsigned)splits);
-  gemm_tma_kernel<BN, STAGES><<<grid, TM_THREADS, SM::TOTAL, st>>>(d, tmA, w.tmap[slot], g);
+  // many short tiles: one persistent CTA per SM with a continuous stage ring and double-buffered accumulators
+  // (DCS_DEBUG_TMA_PERSIST=0: always the one-tile-per-CTA kernel)
+  bool launched = false;
+  if constexpr (BN <= 64) {
+    // measured (profiles/r2_notes.md): the persistent kernel wins where a tile is a handful of k-blocks and there are
+    // many of them -- the tap-clipped transposed convolutions (DSD100 0.153 -> 0.139 ms, Bach10 9.7 -> 7.4 ms); it
+    // loses on long-K tiles (iKala's 200-tap transposed conv: two interleaved CTAs per SM hide more) and on the
+    // store-heavy decoder dense layer (eight epilogue warps per SM beat four)
+    const bool short_tiles = d.kc_rows > 0 && num_kb <= 32;
+    if (ctx->tma_persist && splits == 1 && short_tiles && tiles >= (int64_t)ctx->tma_persist * ctx->num_sms) {
+      constexpr int PST = BN == 32 ? 5 : 4;      // 5 x 40 KB / 4 x 48 KB of stages: one CTA per SM
+      using PSM = TmSmem<BN, PST>;
+      DCS_TRY(ensure_smem_attr(gemm_tma_persist_kernel<BN, PST>, PSM::TOTAL));
+      const int tiles_y = (int)ceil_div64(d.N, BN);
+      const unsigned ctas = (unsigned)std::min<int64_t>(tiles, ctx->num_sms);
+      gemm_tma_persist_kernel<BN, PST><<<ctas, TP_THREADS, PSM::TOTAL, st>>>(d, tmA, w.tmap[slot], g, (int)gx, tiles_y);
+      launched = true;
+    }
+  }
+  if (!launched) {
+    dim3 grid((unsigned)gx, (unsigned)ceil_div64(d.N, BN), (unsigned)splits);
+    gemm_tma_kernel<BN, STAGES><<<grid, TM_THREADS, SM::TOTAL, st>>>(d, tmA, w.tmap[slot], g);
+  }
   DCS_CHECK_LAUNCH();
   ctx->launches++;
   if (splits > 1) DCS_TRY(launch_splitk_reduce(ctx, d, g.partial, g.ldp, splits, st));

@@ -129,7 +129,7 @@ sconv_mask_tc_kernel(const SconvMaskArgs a, const __grid_constant__ CUtensorMap 
 
   if (warp == 5) {
     // ------------------------------------------------------------------ copy engine (un-pooled nets)
-    if (!POOL && lane == 0) {
+    if (!POOL && elect_one()) {
       int it = 0;
       for (int t = t_begin; t < t_end; ++t) {
         int k_lo, k_hi;
@@ -207,7 +207,7 @@ sconv_mask_tc_kernel(const SconvMaskArgs a, const __grid_constant__ CUtensorMap 
     }
   } else if (warp == 4) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = make_idesc_tf32(ST_ROWS, NB);
       const uint32_t b_hi = smem_u32(sB), b_lo = b_hi + TL::B_PLANE;
       int it = 0, sl = 0;

@@ -27,6 +27,22 @@ constexpr uint32_t SBO = 1024;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a converged warp (elect.sync).  Guarding the single-thread issue loops (tcgen05.mma, TMA) with THIS
+// instead of `lane == 0` matters for code quality: ptxas knows exactly one thread runs the region and keeps
+// descriptors, TMEM addresses and predicates in uniform registers; with `lane == 0` it wrapped every UTCHMMA in a
+// loop over the distinct operand values of the warp (~25 instructions per MMA, which bounded the short GEMMs).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- mbarrier -------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -86,6 +102,18 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const void* tmap, uint64_
   asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
                    smem_u32(dst)),
                "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
+// L2 prefetch of a box the copy engine will fetch later (no shared memory, no barrier): takes the HBM latency of a
+// tile's first touch off the stage pipeline
+__device__ __forceinline__ void tma_prefetch_2d(const void* tmap, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_4d(const void* tmap, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0),
+               "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
 
@@ -159,6 +187,13 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
          ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 constexpr uint32_t KSTEP_BYTES = 32;  // descriptor start-address advance per k-step (8 tf32)
+// The same descriptor split into its constant high word and the low word that carries the start address: the MMA
+// issuing thread then advances a descriptor with ONE 32-bit add (stage offset, k-step) instead of rebuilding the
+// 64-bit value -- the issue loop, not the tensor pipe, bounded the short GEMMs (profiles/r2_notes.md).
+constexpr uint32_t DESC_HI = (uint32_t)(SBO >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint64_t desc_of(uint32_t lo) { return ((uint64_t)DESC_HI << 32) | lo; }
+constexpr uint32_t KSTEP_DESC = KSTEP_BYTES >> 4;   // low-word advance per k-step
 // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), both
 // K-major, N>>3 at [17,23), M>>4 at [24,29)
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {

@@ -8,8 +8,10 @@ least-squares projections whose normal equations are made of correlation lags |m
 
   * libdcs computes every needed lag in float64 on the device (`dcs_xcorr_lags`, csrc/bsseval.cu):
     source x source (Gram matrix blocks), source x estimate (right-hand sides), estimate energy;
-  * this module assembles the (nsrc*flen)^2 block-Toeplitz Gram matrix, solves it once per
-    estimate (and its diagonal blocks for the single-source projections) and forms the ratios.
+  * this module assembles the (nsrc*flen)^2 block-Toeplitz Gram matrix, factors it ONCE (and each diagonal
+    block once, for the single-source projections) with a float64 Cholesky on the GPU the lags came from
+    (torch.linalg -> cuSOLVER: a library call, this is evaluation tooling, not the separation hot path), solves
+    for all estimates together and forms the ratios on the host.
 
 No filtering pass is needed: P_j (projection on source j's delays) and P_all (on all sources') are
 orthogonal projections with span_j inside span_all, so with c = G^-1 D
@@ -50,6 +52,35 @@ def _solve(G, D):
         return np.linalg.lstsq(G, D, rcond=None)[0]
 
 
+def _quad_forms(G, D, blocks, device=None):
+    """D' G^-1 D for every column of D [n, m], for the whole Gram matrix and for each diagonal block (list of
+    slices): ONE factorisation per matrix, shared by all right-hand sides (the reference re-solves per estimate,
+    bss_eval_sources.m:147-159).  device = a torch CUDA device: float64 Cholesky + triangular solves on the GPU
+    (torch.linalg -> cuSOLVER; the (nsrc*512)^2 systems took 13x the time of the device lag kernel on the host,
+    profiles/r2/bsseval_split_host_solve.json); None: numpy on the host (CPU tests).  A singular Gram matrix
+    (silent or duplicated source; MATLAB warns and carries on) falls back to least squares on the host."""
+    D = np.asarray(D, dtype=np.float64).reshape(G.shape[0], -1)
+    out = []
+    if device is not None:
+        import torch
+        Gt = torch.as_tensor(G, dtype=torch.float64, device=device)
+        Dt = torch.as_tensor(D, dtype=torch.float64, device=device)
+        for sl in [slice(0, G.shape[0])] + list(blocks):
+            Gs, Ds = Gt[sl, sl], Dt[sl]
+            L, info = torch.linalg.cholesky_ex(Gs)
+            if int(info) == 0:
+                y = torch.linalg.solve_triangular(L, Ds, upper=False)
+                out.append((y * y).sum(dim=0).cpu().numpy())
+            else:
+                c = np.linalg.lstsq(G[sl, sl], D[sl], rcond=None)[0]
+                out.append(np.einsum("ij,ij->j", c, D[sl]))
+        return out[0], out[1:]
+    for sl in [slice(0, G.shape[0])] + list(blocks):
+        c = _solve(G[sl, sl], D[sl])
+        out.append(np.einsum("ij,ij->j", c, D[sl]))
+    return out[0], out[1:]
+
+
 def pair_list(n):
     """the signal pairs whose lags the metric needs, as (kind, i, j) with kind 'ss' (true sources i >= j),
     'se' (true source i, estimate j) or 'ee' (estimate i with itself), and the index of each"""
@@ -59,7 +90,7 @@ def pair_list(n):
     return pairs, {p if p[0] != "ee" else ("ee", p[1]): q for q, p in enumerate(pairs)}
 
 
-def ratios_from_lags(R, idx, n, flen):
+def ratios_from_lags(R, idx, n, flen, device=None):
     """host part: Gram matrix, solves, energy ratios and the best ordering from the lag table R
     [npairs, 2*flen-1] of `pair_list(n)` -> (SDR, SIR, SAR, perm)"""
     # Gram matrix: block (k1, k2), entry (a, b) = sum_t s_k1[t-a] s_k2[t-b] = R_ss[k1,k2][(b-a) + flen-1]
@@ -72,15 +103,16 @@ def ratios_from_lags(R, idx, n, flen):
             G[k2 * flen:(k2 + 1) * flen, k1 * flen:(k1 + 1) * flen] = blk.T
     SDR, SIR, SAR = (np.zeros((n, n)) for _ in range(3))
     zero = np.float64(0.0)
+    # D[:, jest][k*flen + a] = sum_t s_k[t-a] se_jest[t] = R_se[k,jest][flen-1-a]
+    Dm = np.stack([np.concatenate([R[idx["se", k, jest]][flen - 1::-1] for k in range(n)]) for jest in range(n)], axis=1)
+    blocks = [slice(j * flen, (j + 1) * flen) for j in range(n)]
+    p_all_v, p_j_m = _quad_forms(G, Dm, blocks, device)
     with np.errstate(divide="ignore", invalid="ignore"):
         for jest in range(n):
-            # D[k*flen + a] = sum_t s_k[t-a] se[t] = R_se[k,jest][flen-1-a]
-            D = np.concatenate([R[idx["se", k, jest]][flen - 1::-1] for k in range(n)])
             e_se = np.float64(R[idx["ee", jest]][flen - 1])
-            p_all = np.float64(_solve(G, D) @ D)
+            p_all = np.float64(p_all_v[jest])
             for jtrue in range(n):
-                b = slice(jtrue * flen, (jtrue + 1) * flen)
-                p_j = np.float64(_solve(G[b, b], D[b]) @ D[b])
+                p_j = np.float64(p_j_m[jtrue][jest])
                 SDR[jest, jtrue] = 10 * np.log10(p_j / np.maximum(e_se - p_j, zero))
                 SIR[jest, jtrue] = 10 * np.log10(p_j / np.maximum(p_all - p_j, zero))
                 SAR[jest, jtrue] = 10 * np.log10(p_all / np.maximum(e_se - p_all, zero))
@@ -115,7 +147,7 @@ def bss_eval_sources(est, ref, flen=FLEN, ctx=None, stream=None):
     sig = {"ss": (ref, ref), "se": (ref, est), "ee": (est, est)}
     pairs = [(sig[k][0][i], sig[k][1][j]) for k, i, j in kinds]
     R = xcorr_lags(ctx, pairs, L, flen, stream)
-    return ratios_from_lags(R, idx, n, flen)
+    return ratios_from_lags(R, idx, n, flen, device=ref.device)
 
 
 # ------------------------------------------------------------------------ multichannel images, windowed
@@ -129,7 +161,7 @@ def image_pair_list(nsrc, nchan):
     return pairs, {p if p[0] != "ee" else ("ee", p[1]): q for q, p in enumerate(pairs)}
 
 
-def images_from_lags(R, idx, nsrc, nchan, flen):
+def images_from_lags(R, idx, nsrc, nchan, flen, device=None):
     """host part of bss_eval_images (DSD100_eval_only.m:240-306) from the lag table of `image_pair_list`
     -> (SDR, ISR, SIR, SAR), each [nsrc]"""
     K = nsrc * nchan
@@ -142,18 +174,20 @@ def images_from_lags(R, idx, nsrc, nchan, flen):
             G[b * flen:(b + 1) * flen, a * flen:(a + 1) * flen] = blk.T
     out = np.zeros((4, nsrc))
     zero = np.float64(0.0)
+    # one right-hand side per estimate image e = (source j, channel i); one factorisation of G and of each source's block
+    Dm = np.stack([np.concatenate([R[idx["se", r, e]][flen - 1::-1] for r in range(K)]) for e in range(K)], axis=1)
+    blocks = [slice(j * nchan * flen, (j + 1) * nchan * flen) for j in range(nsrc)]
+    p_all_v, p_j_m = _quad_forms(G, Dm, blocks, device)
     with np.errstate(divide="ignore", invalid="ignore"):
         for j in range(nsrc):
-            rows = slice(j * nchan * flen, (j + 1) * nchan * flen)          # source j's channels
             e_se = e_true = cross = p_j = p_all = zero
             for i in range(nchan):
                 e = j * nchan + i
-                D = np.concatenate([R[idx["se", r, e]][flen - 1::-1] for r in range(K)])
                 e_se = e_se + R[idx["ee", e]][flen - 1]
                 e_true = e_true + R[idx["ss", e, e]][flen - 1]              # |s_j,i|^2
-                cross = cross + D[e * flen]                                 # <se_i, s_j,i>  (delay 0)
-                p_all = p_all + _solve(G, D) @ D
-                p_j = p_j + _solve(G[rows, rows], D[rows]) @ D[rows]
+                cross = cross + Dm[e * flen, e]                             # <se_i, s_j,i>  (delay 0)
+                p_all = p_all + p_all_v[e]
+                p_j = p_j + p_j_m[j][e]
             out[0, j] = 10 * np.log10(e_true / np.maximum(e_se - 2 * cross + e_true, zero))
             out[1, j] = 10 * np.log10(e_true / np.maximum(p_j - 2 * cross + e_true, zero))
             out[2, j] = 10 * np.log10(p_j / np.maximum(p_all - p_j, zero))
@@ -182,7 +216,7 @@ def bss_eval_images(est, ref, flen=FLEN, ctx=None, stream=None):
     kinds, idx = image_pair_list(nsrc, nchan)
     sig = {"ss": (ref, ref), "se": (ref, est), "ee": (est, est)}
     pairs = [(sig[k][0][a // nchan, a % nchan], sig[k][1][b // nchan, b % nchan]) for k, a, b in kinds]
-    return images_from_lags(xcorr_lags(ctx, pairs, L, flen, stream), idx, nsrc, nchan, flen)
+    return images_from_lags(xcorr_lags(ctx, pairs, L, flen, stream), idx, nsrc, nchan, flen, device=ref.device)
 
 
 def bss_eval_windowed(est, ref, win, ove, flen=FLEN, ctx=None, stream=None):

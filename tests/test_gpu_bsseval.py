@@ -102,12 +102,19 @@ def test_bss_eval_windowed_images_matches_oracle_on_device_lags():
     R = evaluation.xcorr_lags(ctx, pairs, L2, 512)
     t_lags = time.perf_counter() - t0
     t0 = time.perf_counter()
-    r = evaluation.images_from_lags(R, idx, nsrc2, 2, 512)
+    r_host = evaluation.images_from_lags(R, idx, nsrc2, 2, 512)                      # numpy on the host
     t_host = time.perf_counter() - t0
+    evaluation.images_from_lags(R, idx, nsrc2, 2, 512, device=se2.device)            # warm-up (cuSOLVER handles)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    r = evaluation.images_from_lags(R, idx, nsrc2, 2, 512, device=se2.device)        # float64 Cholesky on the GPU
+    t_dev = time.perf_counter() - t0
     assert all(np.isfinite(x).all() for x in r)
+    for a, b in zip(r, r_host):
+        assert np.max(np.abs(a - b)) < 1e-6
     # algorithmic work of the lag kernel: every pair reads its two signals once per 4-lag group
     rec = {"case": "bss_eval_images, 4 stereo sources, one 30 s window, 512 taps", "pairs": len(pairs),
-           "device_lags_s": t_lags, "host_gram_solve_s": t_host,
+           "device_lags_s": t_lags, "host_gram_and_solve_s": t_host, "gram_on_host_plus_device_cholesky_s": t_dev,
            "lag_macs": len(pairs) * 1023 * float(L2), "lag_fp64_gflops": 2 * len(pairs) * 1023 * float(L2) / t_lags / 1e9}
     os.makedirs(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out"), exist_ok=True)
     with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "bsseval_r2.json"), "w") as f:
