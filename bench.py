@@ -6,8 +6,9 @@
 
 One "step" = one pass of the hot path (STFT -> encoder/decoder -> soft mask + cross-fade ->
 iSTFT/OLA) over one batch of synthetic mono 44.1 kHz mixtures per GPU.  `--config` picks the workload:
-  dsd2048 (default)  BASELINE.json configs[1] (and [3] under torchrun): DSD100 4 sources, frameSize 2048,
-                     hop 512, time_context 30, overlap 25, 8 clips x 180 s per step per GPU
+  dsd2048 (default)  BASELINE.json configs[1] (and, under torchrun with 8 ranks, literally configs[3]: 256 three-minute
+                     mixtures sharded over 8 GPUs): DSD100 4 sources, frameSize 2048, hop 512, time_context 30,
+                     overlap 25, 32 clips x 180 s per step per GPU
   dsd1024            the same net at the frame size the reference's DSD100 scripts really use
   bach10             configs[2]: Bach10 4 instruments, frameSize 4096, blackmanharris, 8 x 30 s
   bach10_score       configs[4]: score-informed Bach10 (4-channel input from score filters), 4 x 30 s
@@ -42,9 +43,9 @@ _emit = print
 UNIT = "audio-s/s"
 
 CONFIGS = {
-    "dsd2048": dict(arch="dsd", N=2048, window="hanning", overlap=25, patcher="standalone", scale=0.3, seconds=180.0, clips=8,
+    "dsd2048": dict(arch="dsd", N=2048, window="hanning", overlap=25, patcher="standalone", scale=0.3, seconds=180.0, clips=32,
                     nsrc=4, baseline="BASELINE configs[1]: DSD100 4-source separation"),
-    "dsd1024": dict(arch="dsd", N=1024, window="hanning", overlap=25, patcher="standalone", scale=0.3, seconds=180.0, clips=8,
+    "dsd1024": dict(arch="dsd", N=1024, window="hanning", overlap=25, patcher="standalone", scale=0.3, seconds=180.0, clips=32,
                     nsrc=4, baseline="BASELINE configs[1] at the frame size of the reference's own DSD100 scripts"),
     "bach10": dict(arch="bach10", N=4096, window="blackmanharris", overlap=25, patcher="standalone", scale=0.3, seconds=30.0,
                    clips=8, nsrc=4, baseline="BASELINE configs[2]: Bach10 4-instrument separation"),

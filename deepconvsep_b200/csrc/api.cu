@@ -122,6 +122,8 @@ int dcs_create(int device, dcs_ctx** out) {
   if (tp && tp[0] >= '0' && tp[0] <= '9') c->tma_prefetch = atoi(tp);
   const char* tr = getenv("DCS_DEBUG_TMA_PROBE");
   if (tr && tr[0] >= '0' && tr[0] <= '9') c->tma_probe = atoi(tr);
+  const char* tu = getenv("DCS_DEBUG_TMA_ATM");
+  if (tu && tu[0] >= '0' && tu[0] <= '9') c->tma_atm = atoi(tu);
   const char* tq = getenv("DCS_DEBUG_TMA_PERSIST");
   if (tq && tq[0] >= '0' && tq[0] <= '9') c->tma_persist = atoi(tq);
   const char* ty = getenv("DCS_DEBUG_TMA_SYNC");

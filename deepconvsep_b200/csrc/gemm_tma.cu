@@ -527,6 +527,262 @@ gemm_tma_persist_kernel(const GemmDesc d, const __grid_constant__ CUtensorMap tm
   }
 }
 
+// ---- persistent variant with the A operand in tensor memory ------------------------------------
+// What bounded the kernels above is shared-memory bandwidth: per k-block the copy engine writes the tile, the low-plane
+// warps read it and write the low plane back, and each of the twelve MMAs fetches 4 KB of A and BN/32 KB of B again.
+// Here the four warps that already pull the raw tile through registers write BOTH planes to tensor memory instead
+// (tcgen05.st, thread = row = TMEM lane) and the MMAs take A from there: shared memory carries the TMA fill, one
+// read of the raw tile and the B fetches only (136 -> 72 KB per k-block at BN = 64).
+constexpr int TA_THREADS = 10 * 32;   // warps 0-3 epilogue, 4 MMA, 5 copy engine, 6-9 A writers
+
+template <int BN, int STAGES>
+struct TmSmemAtm {
+  static constexpr int A_BYTES = TM_BM * ROW_BYTES;  // 16 KB raw tile
+  static constexpr int B_BYTES = BN * ROW_BYTES;
+  static constexpr int STAGE_BYTES = A_BYTES + 2 * B_BYTES;   // A raw, B hi, B lo
+  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TA_THREADS, 1)
+gemm_tma_atm_kernel(const GemmDesc d, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                        const TmaGemmArgs g, int tiles_x, int tiles_y) {
+  using SM = TmSmemAtm<BN, STAGES>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = align1024(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + SM::BAR_OFF);    // TMA landed (raw A tile + both B planes)
+  uint64_t* empty = full + STAGES;                                      // MMAs that read the stage's B planes retired
+  uint64_t* a_ready = empty + STAGES;        // [4] both A planes of a k-block are in tensor memory
+  uint64_t* a_free = a_ready + 4;            // [4] the MMAs that read them retired
+  uint64_t* tmem_full = a_free + 4;          // [2]
+  uint64_t* tmem_empty = tmem_full + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_kdg = (g.n_kd + g.kdb - 1) / g.kdb;
+  const int per_u = g.tiles_pos * n_kdg;
+  const int64_t total_tiles = (int64_t)tiles_x * tiles_y;
+  const uint32_t a_tx = (uint32_t)(g.pb * g.tb * g.kdb) * ROW_BYTES;
+  // 512 TMEM columns: two accumulator sets + a two-deep ring of A operand planes (hi, lo: 2 x 32 columns each).
+  // BN = 64: 2 x 3 accumulators (2 main + 1 correction); BN = 32: 2 x 4 (3 main + 1 correction)
+  constexpr int NACC = BN == 64 ? 3 : 4;
+  const int n_main = g.acc_mode == 2 ? NACC - 1 : 1;
+  const int corr_acc = g.acc_mode == 0 ? 0 : n_main;
+  constexpr uint32_t SET_COLS = NACC * BN;
+  constexpr uint32_t A_COL0 = 2 * SET_COLS;
+  constexpr int ASLOTS = (512 - (int)A_COL0) / 64;      // A ring depth in tensor memory: 2 (BN 64) or 4 (BN 32)
+
+  // tile id -> (first output time / plane / position of the tile, first output column, k-block range)
+  struct Tile { int u, kd, r0, n0, kb_lo, num_kb; };
+  auto decode = [&](int64_t t) {
+    Tile x;
+    const int bx = (int)(t / tiles_y);
+    x.n0 = (int)(t - (int64_t)bx * tiles_y) * BN;
+    const int ug = bx / per_u;
+    const int kdg = (bx - ug * per_u) / g.tiles_pos;
+    x.u = ug * g.tb;
+    x.kd = kdg * g.kdb;
+    x.r0 = (bx - ug * per_u - kdg * g.tiles_pos) * g.pb;
+    int kb_lo = 0, kb_hi = (d.K + KSTAGE - 1) / KSTAGE;
+    if (d.kc_rows > 0) {
+      const int q_lo = max(0, d.kc_pad - x.u), q_hi = min(d.kc_taps - 1, d.kc_pad + d.kc_n - 1 - x.u);
+      kb_lo = (d.kc_unit * q_lo) / KSTAGE;
+      kb_hi = min(kb_hi, (d.kc_unit * (q_hi + 1) + KSTAGE - 1) / KSTAGE);
+      if (kb_hi <= kb_lo) kb_hi = kb_lo + 1;
+    }
+    x.kb_lo = kb_lo;
+    x.num_kb = kb_hi - kb_lo;
+    return x;
+  };
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(&a_ready[s], TM_SPLIT_WARPS * 32);
+      mbar_init(&a_free[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 5 && lane == 0) {
+    prefetch_tensormap(&tmA);
+    prefetch_tensormap(&tmB);
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, 512);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 5) {
+    if (elect_one()) {
+      // ---------------------------------------------------------------- copy engine
+      int it = 0;
+      for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const Tile x = decode(t);
+        for (int kb = 0; kb < x.num_kb; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+          uint8_t* st = smem + s * SM::STAGE_BYTES;
+          const int k0 = (x.kb_lo + kb) * KSTAGE;
+          mbar_arrive_expect_tx(&full[s], a_tx + 2 * SM::B_BYTES);
+          if (g.conv) {
+            const int q = (x.kb_lo + kb) / g.kw, w = (x.kb_lo + kb) - q * g.kw;
+            tma_load_4d(st, &tmA, &full[s], 0, x.r0 + w, x.u + q, x.kd);
+          } else {
+            tma_load_2d(st, &tmA, &full[s], x.u * g.col_per_u + k0, x.r0);
+          }
+          tma_load_2d(st + SM::A_BYTES, &tmB, &full[s], k0, x.n0);
+          tma_load_2d(st + SM::A_BYTES + SM::B_BYTES, &tmB, &full[s], k0, g.Np + x.n0);
+        }
+      }
+    }
+  } else if (warp == 4) {
+    if (elect_one()) {
+      // ---------------------------------------------------------------- MMA issuer
+      constexpr uint32_t idesc = make_idesc_tf32(TM_BM, BN);
+      constexpr uint32_t ST_D = SM::STAGE_BYTES >> 4, A_D = SM::A_BYTES >> 4, B_D = SM::B_BYTES >> 4;
+      const uint32_t lo0 = desc_lo(smem_u32(smem));
+      int it = 0, ti = 0;
+      for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+        const Tile x = decode(t);
+        const int set = ti & 1;
+        const uint32_t acc = tmem_base + set * SET_COLS;
+        mbar_wait(&tmem_empty[set], ((ti >> 1) & 1) ^ 1);
+        fence_after_sync();
+        int ma = 0, ks = 0;
+        const uint32_t t_corr = acc + corr_acc * BN;
+        for (int kb = 0; kb < x.num_kb; ++kb, ++it) {
+          const int s = it % STAGES, as = it % ASLOTS;
+          mbar_wait(&full[s], (it / STAGES) & 1);
+          mbar_wait(&a_ready[as], (it / ASLOTS) & 1);
+          fence_after_sync();
+          const uint32_t b_hi = lo0 + s * ST_D + A_D, b_lo = b_hi + B_D;
+          const uint32_t ta_hi = tmem_base + A_COL0 + as * 64, ta_lo = ta_hi + 32;
+          // corrections into their own accumulator, the main product rotating over the others
+#pragma unroll
+          for (int j = 0; j < KSTAGE / 8; ++j, ++ks) {
+            umma_tf32_ts(t_corr, ta_hi + 8 * j, desc_of(b_lo + KSTEP_DESC * j), idesc, ks != 0);
+            umma_tf32_ts(t_corr, ta_lo + 8 * j, desc_of(b_hi + KSTEP_DESC * j), idesc, 1);
+            umma_tf32_ts(acc + ma * BN, ta_hi + 8 * j, desc_of(b_hi + KSTEP_DESC * j), idesc, corr_acc == 0 ? 1 : (ks >= n_main));
+            ma = ma + 1 == n_main ? 0 : ma + 1;
+          }
+          umma_commit(&empty[s]);
+          umma_commit(&a_free[as]);
+        }
+        umma_commit(&tmem_full[set]);
+      }
+    }
+  } else if (warp > 5) {
+    // ------------------------------------------------------------------ A operand -> tensor memory
+    // thread = tile row = TMEM lane (a warp may only touch the lane quadrant warp % 4): reads its 128-byte row of the
+    // raw tile (eight swizzled 16-byte chunks), writes hi = trunc_tf32(x) and lo = x - hi as 2 x 32 columns
+    // (two groups of four warps taking alternate k-blocks were tried: slower, 0.124 vs 0.116 ms on DSD100's convT2)
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + A_COL0;
+    int it = 0;
+    for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const Tile x = decode(t);
+      for (int kb = 0; kb < x.num_kb; ++kb, ++it) {
+        const int s = it % STAGES, as = it % ASLOTS;
+        mbar_wait(&full[s], (it / STAGES) & 1);
+        const uint8_t* raw = smem + s * SM::STAGE_BYTES;
+        float hi[32], lo[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 v = *reinterpret_cast<const float4*>(raw + tile_off(row, c));
+          float4 h, l;
+          split4(v, h, l);
+          hi[4 * c] = h.x; hi[4 * c + 1] = h.y; hi[4 * c + 2] = h.z; hi[4 * c + 3] = h.w;
+          lo[4 * c] = l.x; lo[4 * c + 1] = l.y; lo[4 * c + 2] = l.z; lo[4 * c + 3] = l.w;
+        }
+        mbar_wait(&a_free[as], ((it / ASLOTS) & 1) ^ 1);
+        fence_after_sync();
+        tmem_st32(lane_base + as * 64, hi);
+        tmem_st32(lane_base + as * 64 + 32, lo);
+        tmem_wait_st();
+        fence_before_sync();
+        mbar_arrive(&a_ready[as]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (thread = tile row = TMEM lane)
+    int ti = 0;
+    for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
+      const Tile x = decode(t);
+      const int set = ti & 1;
+      const int n_main_used = min(n_main, x.num_kb * (KSTAGE / 8));
+      const int pos = x.r0 + tid % g.pb, t2 = tid / g.pb, tl = t2 % g.tb, kdl = t2 / g.tb;
+      const int64_t m64 = (int64_t)(x.u + tl) * g.m_inner + (int64_t)(x.kd + kdl) * g.n_pos + pos;
+      const bool m_ok = kdl < g.kdb && x.kd + kdl < g.n_kd && x.u + tl < g.n_u && pos < g.n_pos && m64 < d.M;
+      const int m = m_ok ? (int)m64 : 0;
+      const int64_t roff = gemm_c_row_offset(d, m);
+      const bool st_ok = m_ok && roff >= 0;
+      mbar_wait_relaxed(&tmem_full[set], (ti >> 1) & 1);
+      fence_after_sync();
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + set * SET_COLS;
+      const int n0 = x.n0;
+#pragma unroll 1
+      for (int j = 0; j < BN / 16; ++j) {
+        const bool live = n0 + 16 * j < d.N;  // warp-uniform
+        float v[16];
+        if (live) {
+          tmem_ld16(taddr + 16 * j, v);
+          for (int a = 1; a < n_main_used; ++a) {
+            float w[16];
+            tmem_ld16(taddr + a * BN + 16 * j, w);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += w[i];
+          }
+          if (corr_acc) {
+            float w[16];
+            tmem_ld16(taddr + corr_acc * BN + 16 * j, w);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += w[i];
+          }
+        }
+        if (j == BN / 16 - 1) {   // every column of this set has been read: the MMA warp may start tile i+2 in it
+          fence_before_sync();
+          mbar_arrive(&tmem_empty[set]);
+        }
+        if (live && st_ok) {
+#pragma unroll
+          for (int i4 = 0; i4 < 4; ++i4) {
+            const int n = n0 + 16 * j + 4 * i4;
+            float e4[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              e4[e] = v[4 * i4 + e];
+              if (d.bias && n + e < d.N) e4[e] += __ldg(d.bias + n + e);
+              if (d.relu) e4[e] = fmaxf(e4[e], 0.f);
+            }
+            if (g.cvec && n + 4 <= d.N) {
+              *reinterpret_cast<float4*>(d.C + roff + (int64_t)(n / d.n_seg) * d.n_ss + (n % d.n_seg)) = make_float4(e4[0], e4[1], e4[2], e4[3]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (n + e < d.N) d.C[roff + (int64_t)((n + e) / d.n_seg) * d.n_ss + ((n + e) % d.n_seg)] = e4[e];
+            }
+          }
+        }
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 4) {
+    fence_after_sync();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // ---- host side ------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -737,14 +993,21 @@ static int launch_tma(dcs_ctx* ctx, const GemmDesc& d, const TcWeight& w, cudaSt
     // many of them -- the tap-clipped transposed convolutions (DSD100 0.153 -> 0.139 ms, Bach10 9.7 -> 7.4 ms); it
     // loses on long-K tiles (iKala's 200-tap transposed conv: two interleaved CTAs per SM hide more) and on the
     // store-heavy decoder dense layer (eight epilogue warps per SM beat four)
-    const bool short_tiles = d.kc_rows > 0 && num_kb <= 32;
+    const bool short_tiles = num_kb <= 32 && d.N <= 64;   // (the launcher's num_kb is the un-clipped count)
     if (ctx->tma_persist && splits == 1 && short_tiles && tiles >= (int64_t)ctx->tma_persist * ctx->num_sms) {
-      constexpr int PST = BN == 32 ? 5 : 4;      // 5 x 40 KB / 4 x 48 KB of stages: one CTA per SM
-      using PSM = TmSmem<BN, PST>;
-      DCS_TRY(ensure_smem_attr(gemm_tma_persist_kernel<BN, PST>, PSM::TOTAL));
       const int tiles_y = (int)ceil_div64(d.N, BN);
       const unsigned ctas = (unsigned)std::min<int64_t>(tiles, ctx->num_sms);
-      gemm_tma_persist_kernel<BN, PST><<<ctas, TP_THREADS, PSM::TOTAL, st>>>(d, tmA, w.tmap[slot], g, (int)gx, tiles_y);
+      if (ctx->tma_atm) {     // A operand in tensor memory (DCS_DEBUG_TMA_ATM=0: both planes through shared memory)
+        constexpr int AST = 6;                   // 6 x 32 KB (BN 64) / 6 x 24 KB (BN 32) of stages
+        using ASM_ = TmSmemAtm<BN, AST>;
+        DCS_TRY(ensure_smem_attr(gemm_tma_atm_kernel<BN, AST>, ASM_::TOTAL));
+        gemm_tma_atm_kernel<BN, AST><<<ctas, TA_THREADS, ASM_::TOTAL, st>>>(d, tmA, w.tmap[slot], g, (int)gx, tiles_y);
+      } else {
+        constexpr int PST = BN == 32 ? 5 : 4;      // 5 x 40 KB / 4 x 48 KB of stages: one CTA per SM
+        using PSM = TmSmem<BN, PST>;
+        DCS_TRY(ensure_smem_attr(gemm_tma_persist_kernel<BN, PST>, PSM::TOTAL));
+        gemm_tma_persist_kernel<BN, PST><<<ctas, TP_THREADS, PSM::TOTAL, st>>>(d, tmA, w.tmap[slot], g, (int)gx, tiles_y);
+      }
       launched = true;
     }
   }
