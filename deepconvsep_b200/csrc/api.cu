@@ -122,6 +122,8 @@ int dcs_create(int device, dcs_ctx** out) {
   if (tp && tp[0] >= '0' && tp[0] <= '9') c->tma_prefetch = atoi(tp);
   const char* tr = getenv("DCS_DEBUG_TMA_PROBE");
   if (tr && tr[0] >= '0' && tr[0] <= '9') c->tma_probe = atoi(tr);
+  const char* tw = getenv("DCS_DEBUG_TMA_PERSIST_WIDE");
+  if (tw && tw[0] >= '0' && tw[0] <= '9') c->tma_persist_wide = atoi(tw);
   const char* tu = getenv("DCS_DEBUG_TMA_ATM");
   if (tu && tu[0] >= '0' && tu[0] <= '9') c->tma_atm = atoi(tu);
   const char* tq = getenv("DCS_DEBUG_TMA_PERSIST");

@@ -76,6 +76,7 @@ struct dcs_ctx {
   bool tma_sync = false; // DCS_DEBUG_TMA_SYNC: synchronise after each TMA GEMM
   int tma_prefetch = 0;  // DCS_DEBUG_TMA_PREFETCH: activation boxes prefetched into L2 ahead of the stage ring (measured: no gain)
   int tma_probe = 0;     // DCS_DEBUG_TMA_PROBE: timing experiments on the TMA GEMM (results are wrong)
+  int tma_persist_wide = 1;   // DCS_DEBUG_TMA_PERSIST_WIDE: persistent kernel also for N > 64 (Bach10 decoder dense 2.86 -> 2.57 ms, DSD100 neutral)
   int tma_atm = 1;       // DCS_DEBUG_TMA_ATM: persistent GEMM takes its A operand from tensor memory (0: from shared memory)
   int tma_persist = 8;   // DCS_DEBUG_TMA_PERSIST: persistent GEMM for short-K tiles when tiles >= this x SMs (0 = never)
   bool debug_smem_fft = false;

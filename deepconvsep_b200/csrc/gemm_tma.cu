@@ -73,6 +73,46 @@ struct TmaGemmArgs {
   float* partial;
 };
 
+// bias / ReLU / store of 16 accumulator columns [n, n+16) of the C row at element offset `roff`.  `seg` (uniform per
+// launch): the C columns are segmented (n_seg < N, the decoder dense layers scattering into the padded buffer) -- only
+// then is the per-group column offset a division; the plain case costs one add.  (The epilogue of the persistent
+// kernels ran 1 224 instructions per warp per 128x32 tile, mostly these divisions: 40 % of all instructions executed
+// by Bach10's InverseLayer(conv2), whose tiles are only ~7 k-blocks long -- profiles/r2_notes.md.)
+__device__ __forceinline__ void gemm_store16(const GemmDesc& d, bool cvec, bool seg, int64_t roff, int n, const float (&v)[16]) {
+  int sq = 0, sr = 0;     // segment / column inside it of the chunk's first column: one division pair per 16 columns
+  if (seg) { sq = n / d.n_seg; sr = n - sq * d.n_seg; }
+#pragma unroll
+  for (int i4 = 0; i4 < 4; ++i4) {
+    const int nn = n + 4 * i4;
+    if (nn >= d.N) break;
+    float x[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) x[e] = v[4 * i4 + e];
+    if (d.bias) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (nn + e < d.N) x[e] += __ldg(d.bias + nn + e);
+    }
+    if (d.relu) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) x[e] = fmaxf(x[e], 0.f);
+    }
+    if (cvec && nn + 4 <= d.N) {   // a group of 4 columns never straddles a C segment (launcher)
+      int q = sq, r = sr + 4 * i4;
+      while (seg && r >= d.n_seg) { r -= d.n_seg; ++q; }      // at most once or twice: n_seg >= 4
+      const int64_t coff = seg ? (int64_t)q * d.n_ss + r : (int64_t)nn;
+      *reinterpret_cast<float4*>(d.C + roff + coff) = make_float4(x[0], x[1], x[2], x[3]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (nn + e < d.N) {
+          const int64_t coff = seg ? (int64_t)((nn + e) / d.n_seg) * d.n_ss + ((nn + e) % d.n_seg) : (int64_t)(nn + e);
+          d.C[roff + coff] = x[e];
+        }
+    }
+  }
+}
+
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(TM_THREADS)
 gemm_tma_kernel(const GemmDesc d, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -89,10 +129,14 @@ gemm_tma_kernel(const GemmDesc d, const __grid_constant__ CUtensorMap tmA, const
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_kdg = (g.n_kd + g.kdb - 1) / g.kdb;
   const int per_u = g.tiles_pos * n_kdg;
-  const int ug = blockIdx.x / per_u;
-  const int kdg = (blockIdx.x - ug * per_u) / g.tiles_pos;
+  // tile order: the output times u of one (plane, position tile) are adjacent -- they re-read the same few input rows
+  // (a transposed convolution reads each input row once per tap), so the re-reads hit L2 instead of HBM.  (u-major order
+  // made Bach10's InverseLayer(conv2) read 30 GB from DRAM for 1.5 GB of input: L2 hit rate 28 %, profiles/r2_notes.md)
+  const int n_ug = (g.n_u + g.tb - 1) / g.tb;
+  const int ug = blockIdx.x % n_ug, rest = blockIdx.x / n_ug;
+  const int kdg = rest / g.tiles_pos;
   const int u = ug * g.tb, kd = kdg * g.kdb;                                   // first output time / plane of the tile
-  const int r0 = (blockIdx.x - ug * per_u - kdg * g.tiles_pos) * g.pb;       // first position / row
+  const int r0 = (rest - kdg * g.tiles_pos) * g.pb;                          // first position / row
   const int n0 = blockIdx.y * BN;
   const uint32_t a_tx = (uint32_t)(g.pb * g.tb * g.kdb) * ROW_BYTES;         // bytes one A box delivers
   int kb_lo = 0, kb_hi = (d.K + KSTAGE - 1) / KSTAGE;
@@ -261,24 +305,7 @@ gemm_tma_kernel(const GemmDesc d, const __grid_constant__ CUtensorMap tmA, const
         for (int i4 = 0; i4 < 4; ++i4)
           if (n0 + 16 * j + 4 * i4 < g.ldp) dst[i4] = make_float4(v[4 * i4], v[4 * i4 + 1], v[4 * i4 + 2], v[4 * i4 + 3]);
       } else if (st_ok) {
-#pragma unroll
-        for (int i4 = 0; i4 < 4; ++i4) {
-          const int n = n0 + 16 * j + 4 * i4;
-          float x[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            x[e] = v[4 * i4 + e];
-            if (d.bias && n + e < d.N) x[e] += __ldg(d.bias + n + e);
-            if (d.relu) x[e] = fmaxf(x[e], 0.f);
-          }
-          if (g.cvec && n + 4 <= d.N) {   // a group of 4 columns never straddles a C segment (launcher)
-            *reinterpret_cast<float4*>(d.C + roff + (int64_t)(n / d.n_seg) * d.n_ss + (n % d.n_seg)) = make_float4(x[0], x[1], x[2], x[3]);
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (n + e < d.N) d.C[roff + (int64_t)((n + e) / d.n_seg) * d.n_ss + ((n + e) % d.n_seg)] = x[e];
-          }
-        }
+        gemm_store16(d, g.cvec != 0, d.n_seg < d.N, roff, n0 + 16 * j, v);
       }
     }
     fence_before_sync();
@@ -331,11 +358,12 @@ gemm_tma_persist_kernel(const GemmDesc d, const __grid_constant__ CUtensorMap tm
     Tile x;
     const int bx = (int)(t / tiles_y);
     x.n0 = (int)(t - (int64_t)bx * tiles_y) * BN;
-    const int ug = bx / per_u;
-    const int kdg = (bx - ug * per_u) / g.tiles_pos;
+    const int n_ug = (g.n_u + g.tb - 1) / g.tb;     // u fastest: see gemm_tma_kernel
+    const int ug = bx % n_ug, rest = bx / n_ug;
+    const int kdg = rest / g.tiles_pos;
     x.u = ug * g.tb;
     x.kd = kdg * g.kdb;
-    x.r0 = (bx - ug * per_u - kdg * g.tiles_pos) * g.pb;
+    x.r0 = (rest - kdg * g.tiles_pos) * g.pb;
     int kb_lo = 0, kb_hi = (d.K + KSTAGE - 1) / KSTAGE;
     if (d.kc_rows > 0) {
       const int q_lo = max(0, d.kc_pad - x.u), q_hi = min(d.kc_taps - 1, d.kc_pad + d.kc_n - 1 - x.u);
@@ -478,44 +506,31 @@ gemm_tma_persist_kernel(const GemmDesc d, const __grid_constant__ CUtensorMap tm
         const bool live = n0 + 16 * j < d.N;  // warp-uniform
         float v[16];
         if (live) {
-          tmem_ld16(taddr + 16 * j, v);
-          for (int a = 1; a < n_main_used; ++a) {
-            float w[16];
-            tmem_ld16(taddr + a * BN + 16 * j, w);
+          // all accumulators of the chunk in flight, one wait (each tcgen05.ld + wait round trip is ~100+ cycles)
+          float w1[16], w2[16], wc[16];
+          tmem_ld16_nowait(taddr + 16 * j, v);
+          if (n_main_used > 1) tmem_ld16_nowait(taddr + BN + 16 * j, w1);
+          if (n_main_used > 2) tmem_ld16_nowait(taddr + 2 * BN + 16 * j, w2);
+          if (corr_acc) tmem_ld16_nowait(taddr + corr_acc * BN + 16 * j, wc);
+          tmem_wait_ld();
+          if (n_main_used > 1) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += w[i];
+            for (int i = 0; i < 16; ++i) v[i] += w1[i];
+          }
+          if (n_main_used > 2) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += w2[i];
           }
           if (corr_acc) {
-            float w[16];
-            tmem_ld16(taddr + corr_acc * BN + 16 * j, w);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += w[i];
+            for (int i = 0; i < 16; ++i) v[i] += wc[i];
           }
         }
         if (j == BN / 16 - 1) {   // every column of this set has been read: the MMA warp may start tile i+2 in it
           fence_before_sync();
           mbar_arrive(&tmem_empty[set]);
         }
-        if (live && st_ok) {
-#pragma unroll
-          for (int i4 = 0; i4 < 4; ++i4) {
-            const int n = n0 + 16 * j + 4 * i4;
-            float e4[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              e4[e] = v[4 * i4 + e];
-              if (d.bias && n + e < d.N) e4[e] += __ldg(d.bias + n + e);
-              if (d.relu) e4[e] = fmaxf(e4[e], 0.f);
-            }
-            if (g.cvec && n + 4 <= d.N) {
-              *reinterpret_cast<float4*>(d.C + roff + (int64_t)(n / d.n_seg) * d.n_ss + (n % d.n_seg)) = make_float4(e4[0], e4[1], e4[2], e4[3]);
-            } else {
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (n + e < d.N) d.C[roff + (int64_t)((n + e) / d.n_seg) * d.n_ss + ((n + e) % d.n_seg)] = e4[e];
-            }
-          }
-        }
+        if (live && st_ok) gemm_store16(d, g.cvec != 0, d.n_seg < d.N, roff, n0 + 16 * j, v);
       }
     }
   }
@@ -533,7 +548,7 @@ gemm_tma_persist_kernel(const GemmDesc d, const __grid_constant__ CUtensorMap tm
 // Here the four warps that already pull the raw tile through registers write BOTH planes to tensor memory instead
 // (tcgen05.st, thread = row = TMEM lane) and the MMAs take A from there: shared memory carries the TMA fill, one
 // read of the raw tile and the B fetches only (136 -> 72 KB per k-block at BN = 64).
-constexpr int TA_THREADS = 10 * 32;   // warps 0-3 epilogue, 4 MMA, 5 copy engine, 6-9 A writers
+constexpr int TA_THREADS = 14 * 32;   // warps 0-3 and 10-13 epilogue, 4 MMA, 5 copy engine, 6-9 A writers
 
 template <int BN, int STAGES>
 struct TmSmemAtm {
@@ -579,11 +594,12 @@ gemm_tma_atm_kernel(const GemmDesc d, const __grid_constant__ CUtensorMap tmA, c
     Tile x;
     const int bx = (int)(t / tiles_y);
     x.n0 = (int)(t - (int64_t)bx * tiles_y) * BN;
-    const int ug = bx / per_u;
-    const int kdg = (bx - ug * per_u) / g.tiles_pos;
+    const int n_ug = (g.n_u + g.tb - 1) / g.tb;     // u fastest: see gemm_tma_kernel
+    const int ug = bx % n_ug, rest = bx / n_ug;
+    const int kdg = rest / g.tiles_pos;
     x.u = ug * g.tb;
     x.kd = kdg * g.kdb;
-    x.r0 = (bx - ug * per_u - kdg * g.tiles_pos) * g.pb;
+    x.r0 = (rest - kdg * g.tiles_pos) * g.pb;
     int kb_lo = 0, kb_hi = (d.K + KSTAGE - 1) / KSTAGE;
     if (d.kc_rows > 0) {
       const int q_lo = max(0, d.kc_pad - x.u), q_hi = min(d.kc_taps - 1, d.kc_pad + d.kc_n - 1 - x.u);
@@ -607,7 +623,7 @@ gemm_tma_atm_kernel(const GemmDesc d, const __grid_constant__ CUtensorMap tmA, c
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 128);
+      mbar_init(&tmem_empty[s], 256);
     }
     fence_barrier_init();
   }
@@ -680,7 +696,7 @@ gemm_tma_atm_kernel(const GemmDesc d, const __grid_constant__ CUtensorMap tmA, c
         umma_commit(&tmem_full[set]);
       }
     }
-  } else if (warp > 5) {
+  } else if (warp > 5 && warp < 10) {
     // ------------------------------------------------------------------ A operand -> tensor memory
     // thread = tile row = TMEM lane (a warp may only touch the lane quadrant warp % 4): reads its 128-byte row of the
     // raw tile (eight swizzled 16-byte chunks), writes hi = trunc_tf32(x) and lo = x - hi as 2 x 32 columns
@@ -714,12 +730,16 @@ gemm_tma_atm_kernel(const GemmDesc d, const __grid_constant__ CUtensorMap tmA, c
     }
   } else {
     // ------------------------------------------------------------------ epilogue (thread = tile row = TMEM lane)
+    // eight warps: warps 0-3 and 10-13 pair up on the four lane quadrants, each taking every other 16-column chunk --
+    // with tiles of ~7 k-blocks the epilogue of a tile, not its main loop, set the pace
+    const int half = warp >= 10 ? 1 : 0;
+    const int erow = (warp & 3) * 32 + lane;
     int ti = 0;
     for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x, ++ti) {
       const Tile x = decode(t);
       const int set = ti & 1;
       const int n_main_used = min(n_main, x.num_kb * (KSTAGE / 8));
-      const int pos = x.r0 + tid % g.pb, t2 = tid / g.pb, tl = t2 % g.tb, kdl = t2 / g.tb;
+      const int pos = x.r0 + erow % g.pb, t2 = erow / g.pb, tl = t2 % g.tb, kdl = t2 / g.tb;
       const int64_t m64 = (int64_t)(x.u + tl) * g.m_inner + (int64_t)(x.kd + kdl) * g.n_pos + pos;
       const bool m_ok = kdl < g.kdb && x.kd + kdl < g.n_kd && x.u + tl < g.n_u && pos < g.n_pos && m64 < d.M;
       const int m = m_ok ? (int)m64 : 0;
@@ -727,51 +747,38 @@ gemm_tma_atm_kernel(const GemmDesc d, const __grid_constant__ CUtensorMap tmA, c
       const bool st_ok = m_ok && roff >= 0;
       mbar_wait_relaxed(&tmem_full[set], (ti >> 1) & 1);
       fence_after_sync();
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + set * SET_COLS;
+      const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + set * SET_COLS;
       const int n0 = x.n0;
 #pragma unroll 1
       for (int j = 0; j < BN / 16; ++j) {
-        const bool live = n0 + 16 * j < d.N;  // warp-uniform
+        const bool live = n0 + 16 * j < d.N && (j & 1) == half;  // warp-uniform
         float v[16];
         if (live) {
-          tmem_ld16(taddr + 16 * j, v);
-          for (int a = 1; a < n_main_used; ++a) {
-            float w[16];
-            tmem_ld16(taddr + a * BN + 16 * j, w);
+          // all accumulators of the chunk in flight, one wait (each tcgen05.ld + wait round trip is ~100+ cycles)
+          float w1[16], w2[16], wc[16];
+          tmem_ld16_nowait(taddr + 16 * j, v);
+          if (n_main_used > 1) tmem_ld16_nowait(taddr + BN + 16 * j, w1);
+          if (n_main_used > 2) tmem_ld16_nowait(taddr + 2 * BN + 16 * j, w2);
+          if (corr_acc) tmem_ld16_nowait(taddr + corr_acc * BN + 16 * j, wc);
+          tmem_wait_ld();
+          if (n_main_used > 1) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += w[i];
+            for (int i = 0; i < 16; ++i) v[i] += w1[i];
+          }
+          if (n_main_used > 2) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += w2[i];
           }
           if (corr_acc) {
-            float w[16];
-            tmem_ld16(taddr + corr_acc * BN + 16 * j, w);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += w[i];
+            for (int i = 0; i < 16; ++i) v[i] += wc[i];
           }
         }
         if (j == BN / 16 - 1) {   // every column of this set has been read: the MMA warp may start tile i+2 in it
           fence_before_sync();
           mbar_arrive(&tmem_empty[set]);
         }
-        if (live && st_ok) {
-#pragma unroll
-          for (int i4 = 0; i4 < 4; ++i4) {
-            const int n = n0 + 16 * j + 4 * i4;
-            float e4[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              e4[e] = v[4 * i4 + e];
-              if (d.bias && n + e < d.N) e4[e] += __ldg(d.bias + n + e);
-              if (d.relu) e4[e] = fmaxf(e4[e], 0.f);
-            }
-            if (g.cvec && n + 4 <= d.N) {
-              *reinterpret_cast<float4*>(d.C + roff + (int64_t)(n / d.n_seg) * d.n_ss + (n % d.n_seg)) = make_float4(e4[0], e4[1], e4[2], e4[3]);
-            } else {
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (n + e < d.N) d.C[roff + (int64_t)((n + e) / d.n_seg) * d.n_ss + ((n + e) % d.n_seg)] = e4[e];
-            }
-          }
-        }
+        if (live && st_ok) gemm_store16(d, g.cvec != 0, d.n_seg < d.N, roff, n0 + 16 * j, v);
       }
     }
   }
@@ -993,7 +1000,7 @@ static int launch_tma(dcs_ctx* ctx, const GemmDesc& d, const TcWeight& w, cudaSt
     // many of them -- the tap-clipped transposed convolutions (DSD100 0.153 -> 0.139 ms, Bach10 9.7 -> 7.4 ms); it
     // loses on long-K tiles (iKala's 200-tap transposed conv: two interleaved CTAs per SM hide more) and on the
     // store-heavy decoder dense layer (eight epilogue warps per SM beat four)
-    const bool short_tiles = num_kb <= 32 && d.N <= 64;   // (the launcher's num_kb is the un-clipped count)
+    const bool short_tiles = num_kb <= 32 && (d.N <= 64 || ctx->tma_persist_wide);   // (num_kb: the un-clipped count)
     if (ctx->tma_persist && splits == 1 && short_tiles && tiles >= (int64_t)ctx->tma_persist * ctx->num_sms) {
       const int tiles_y = (int)ceil_div64(d.N, BN);
       const unsigned ctas = (unsigned)std::min<int64_t>(tiles, ctx->num_sms);

@@ -1,0 +1,9 @@
+#!/bin/bash
+O=$GRAFT_REPO_ROOT/gpurun_out; mkdir -p $O; cd $GRAFT_REPO_ROOT
+timeout 900 python -m pytest tests/test_gpu_gemm.py tests/test_gpu_dsd.py tests/test_gpu_sconv.py tests/test_gpu_ild.py -m gpu -q -x --durations=3 2>&1 | tail -8 > $O/gpu_tests15.log
+timeout 400 python bench.py --steps 10 --clips 8 --no-cpu-baseline --traffic off > $O/bench15_N1.json 2> $O/bench15_N1.err
+timeout 500 python bench.py --config bach10 --steps 5 --no-cpu-baseline --traffic off > $O/bench15_bach10.json 2> $O/bench15_bach10.err
+timeout 500 python bench.py --config bach10_score --steps 5 --no-cpu-baseline --traffic off > $O/bench15_score.json 2> $O/bench15_score.err
+timeout 500 python bench.py --config ikala --steps 5 --no-cpu-baseline --traffic off > $O/bench15_ikala.json 2> $O/bench15_ikala.err
+timeout 500 python bench.py --config dsd1024 --steps 5 --clips 8 --no-cpu-baseline --traffic off > $O/bench15_dsd1024.json 2> $O/bench15_dsd1024.err
+echo run15 done

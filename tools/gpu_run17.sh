@@ -1,0 +1,10 @@
+#!/bin/bash
+O=$GRAFT_REPO_ROOT/gpurun_out; mkdir -p $O; cd $GRAFT_REPO_ROOT
+timeout 900 python -m pytest tests/test_gpu_gemm.py tests/test_gpu_dsd.py tests/test_gpu_sconv.py tests/test_gpu_ild.py -m gpu -q -x --durations=3 2>&1 | tail -8 > $O/gpu_tests17.log
+for W in 0 1; do
+DCS_DEBUG_TMA_PERSIST_WIDE=$W timeout 400 python bench.py --steps 10 --clips 8 --no-cpu-baseline --traffic off > $O/bench17_N1_w$W.json 2> $O/bench17_N1_w$W.err
+DCS_DEBUG_TMA_PERSIST_WIDE=$W timeout 500 python bench.py --config bach10 --steps 5 --no-cpu-baseline --traffic off > $O/bench17_bach10_w$W.json 2> $O/bench17_bach10_w$W.err
+done
+timeout 500 python bench.py --config bach10_score --steps 5 --no-cpu-baseline --traffic off > $O/bench17_score.json 2> $O/bench17_score.err
+timeout 500 python bench.py --config ikala --steps 5 --no-cpu-baseline --traffic off > $O/bench17_ikala.json 2> $O/bench17_ikala.err
+echo run17 done
