@@ -283,6 +283,7 @@ int dcs_model_destroy(dcs_model* m) {
   if (!m) return DCS_OK;
   for (float* d : m->dev) cudaFree(d);
   for (auto& w : m->sc.tW) tc_weight_destroy(&w);
+  tc_weight_destroy(&m->sc.tW1p);
   tc_weight_destroy(&m->tW1f); tc_weight_destroy(&m->tW2c); tc_weight_destroy(&m->tWfc);
   tc_weight_destroy(&m->tWdec); tc_weight_destroy(&m->tWt2);
   delete m;

@@ -72,7 +72,7 @@ struct dcs_ctx {
   int tma_mode = 1;      // DCS_DEBUG_TMA: 0 = register-staged GEMM everywhere, 2 = rewrite the high plane
   int tma_stages = 2;    // DCS_DEBUG_TMA_STAGES (64-wide tiles: 2 or 4)
   bool tma_wide = false; // DCS_DEBUG_TMA_WIDE: 128-wide tiles (one CTA per SM) for N > 64
-  int tma_mask = 31;     // DCS_DEBUG_TMA_MASK: which operand views may take the TMA kernel
+  int tma_mask = 63;     // DCS_DEBUG_TMA_MASK: which operand views may take the TMA kernel (32: the window view of conv1)
   bool tma_sync = false; // DCS_DEBUG_TMA_SYNC: synchronise after each TMA GEMM
   int tma_prefetch = 0;  // DCS_DEBUG_TMA_PREFETCH: activation boxes prefetched into L2 ahead of the stage ring (measured: no gain)
   int tma_probe = 0;     // DCS_DEBUG_TMA_PROBE: timing experiments on the TMA GEMM (results are wrong)
@@ -133,6 +133,7 @@ struct TcWeight {
 struct dcs_sconv {   // strided-conv1 families: iKala (pool / no pool), Bach10
   int nch, sw1, J, pool, WP, kh2, kw2, h2, w2, HP, WPP, ndec, nfc, rule;
   dcs::TcWeight tW[8];                 // 0 conv1, 1 conv2, 2 fc, 3 convT2, 4.. decoder dense layers
+  dcs::TcWeight tW1p;                  // conv1 with a 32-row K pitch per input channel (copy-engine window view)
   float *b1, *b2, *bfc, *bdec[4], *bout, *Wsc;
 };
 struct dcs_model {
@@ -184,6 +185,10 @@ struct GemmDesc {
   int m_inner; int64_t a_so, a_si;
   int m_inner2; int64_t a_s2;
   int k_seg; int64_t k_ss;           // A col offset  = (k / k_seg) * k_ss + (k % k_seg)
+  // optional "window" view for the copy engine (win_stride > 0; conv1 of the 30-channel nets with a 16-byte position
+  // stride): row m = (frame, position j) is the 32-float window starting at frame * a_so + j * win_stride of plane
+  // k / 32 (k_seg = 32, planes k_ss apart); windows overlap and run 2 floats past the 30-tap filter (zero weight rows)
+  int win_stride;
   int64_t ldb;                       // B[k][n] at B + k*ldb + n
   int cm_inner; int64_t c_so, c_si;  // C row offset (same three-level form)
   int cm_inner2; int64_t c_s2;

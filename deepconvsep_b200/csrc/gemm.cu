@@ -106,6 +106,7 @@ GemmDesc gemm_plain(const float* A, int64_t lda, const float* B, int64_t ldb, co
   d.a_valid_rows = M;
   d.m_inner = 1; d.a_so = lda; d.a_si = 0; d.m_inner2 = 1; d.a_s2 = 0;
   d.k_seg = K > 0 ? K : 1; d.k_ss = 0;
+  d.win_stride = 0;
   d.ldb = ldb;
   d.cm_inner = 1; d.c_so = ldc; d.c_si = 0; d.cm_inner2 = 1; d.c_s2 = 0;
   d.n_seg = N > 0 ? N : 1; d.n_ss = 0; d.c_col0 = 0;

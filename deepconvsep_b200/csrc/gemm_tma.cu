@@ -858,6 +858,28 @@ struct TmaView {
 static TmaView classify(const GemmDesc& d) {
   TmaView v;
   if ((uintptr_t)d.A % 16 != 0 || d.M <= 0) return v;
+  if (d.win_stride > 0) {                                 // ---- window mode (strided conv1 of the 30-channel nets)
+    // 4-D map {32 window floats (stride 4 B), positions (stride win_stride), channel plane, frame}; one k-block = one
+    // channel plane: in the conv-mode kernel the "time tap" coordinate walks the planes (q = k-block, u = 0) and the
+    // "plane" coordinate is the frame.  Frames >= a_valid_rows / m_inner are the copy engine's zero fill.
+    if (d.win_stride % 4 != 0 || d.k_seg != KSTAGE || d.K % KSTAGE != 0 || d.m_inner <= 0 || d.a_so % 4 != 0 || d.k_ss % 4 != 0 ||
+        d.kc_rows != 0 || d.a_valid_rows % d.m_inner != 0)
+      return v;
+    const int nseg = d.K / KSTAGE;
+    v.rank = 4;
+    v.dims[0] = KSTAGE; v.dims[1] = (uint64_t)d.m_inner; v.dims[2] = (uint64_t)nseg; v.dims[3] = (uint64_t)(d.a_valid_rows / d.m_inner);
+    v.strides[0] = (uint64_t)d.win_stride * 4;
+    v.strides[1] = (uint64_t)(nseg > 1 ? d.k_ss : d.a_so) * 4;
+    v.strides[2] = (uint64_t)d.a_so * 4;
+    v.n_u = 1; v.kw = 1;
+    v.rows_per_u = d.m_inner;
+    v.n_kd = (int)ceil_div64(d.M, d.m_inner);
+    if (v.dims[3] == 0) return v;
+    v.overlap = true;        // windows overlap (pitch 16 B < 128 B): a driver that refused such a map would mean fallback
+    v.kind = 32;
+    v.mode = 2;
+    return v;
+  }
   if (d.k_seg >= d.K) {                                   // ---- rows mode
     if (d.m_inner2 != 1) return v;
     const bool plain = d.m_inner == 1;
@@ -963,7 +985,7 @@ static int launch_tma(dcs_ctx* ctx, const GemmDesc& d, const TcWeight& w, cudaSt
            (d.n_seg >= d.N || (d.n_seg % 4 == 0 && d.n_ss % 4 == 0));
   alignas(64) CUtensorMap tmA;
   if (v.overlap) {
-    if (encode_map(&tmA, d.A, v.rank, v.dims, v.strides, (uint32_t)v.pb, true) != DCS_OK) {
+    if (encode_map(&tmA, d.A, v.rank, v.dims, v.strides, (uint32_t)v.pb, true, (uint32_t)v.tb, (uint32_t)v.kdb) != DCS_OK) {
       g_overlap_rejected = true;
       return DCS_TMA_FALLBACK;
     }

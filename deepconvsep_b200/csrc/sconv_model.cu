@@ -87,6 +87,13 @@ int model_create_sconv(dcs_model* m, int nparams, const float* const* hp, const 
           Bt2[(((size_t)p * kw2 + q) * CP + fo) * C + ci] = v;                        // InverseLayer: in fo -> out ci
         }
   DCS_TRY(tc_weight_create(B1.data(), C, nch * KW, C, &c.tW[0]));
+  if (c.sw1 % 4 == 0) {   // 16-byte position stride: conv1 can be fed by the copy engine as 32-float windows; K = nch x 32
+    std::vector<float> B1p((size_t)nch * 32 * C, 0.f);    // rows ch*32 + q (q < 30) = B1 rows ch*30 + q; rows 30, 31 zero
+    for (int ch = 0; ch < nch; ++ch)
+      for (int q = 0; q < KW; ++q)
+        memcpy(&B1p[((size_t)ch * 32 + q) * C], &B1[((size_t)ch * KW + q) * C], C * sizeof(float));
+    DCS_TRY(tc_weight_create(B1p.data(), C, nch * 32, C, &c.tW1p));
+  }
   DCS_TRY(tc_weight_create(B2.data(), C, (int)K2, C, &c.tW[1]));
   DCS_TRY(tc_weight_create(Bt2.data(), C, (int)K2, C, &c.tW[3]));
   {  // bottleneck: rows permuted from Lasagne's (f', i, v) flattening to (i, v, f' padded to 32)
@@ -169,7 +176,16 @@ int sconv_forward(dcs_ctx* ctx, dcs_model* m, const float* d_in, int64_t in_plan
     g.m_inner = J; g.a_so = ldf; g.a_si = c.sw1;
     g.k_seg = 30; g.k_ss = in_plane;      // one 30-tap segment per input channel
     g.a_valid_rows = (int)(T * J);
-    DCS_TRY(launch_gemm_tc(ctx, g, c.tW[0], st));
+    int r = DCS_TMA_FALLBACK;
+    if (c.tW1p.hi && ctx->tma_mode && !ctx->debug_simt_gemm && (ctx->tma_mask & 32)) {
+      // copy-engine view: 32-float windows (the two floats past the 30 taps meet zero weight rows)
+      GemmDesc w = gemm_plain(d_in, 0, nullptr, C, c.b1, H1, CP, (int)(Tp * J), C, 32 * c.nch, 0);
+      w.m_inner = J; w.a_so = ldf; w.a_si = c.sw1; w.k_seg = 32; w.k_ss = in_plane; w.a_valid_rows = (int)(T * J);
+      w.win_stride = c.sw1;
+      if (gemm_tma_eligible(w, ctx->tma_mask)) r = launch_gemm_tma(ctx, w, c.tW1p, st);
+    }
+    if (r == DCS_TMA_FALLBACK) r = launch_gemm_tc(ctx, g, c.tW[0], st);   // register-staged kernel (iKala: 12-byte stride)
+    DCS_TRY(r);
   }
   if (c.pool) {
     ProfScope ps(ctx, "enc_maxpool", st);
