@@ -83,3 +83,19 @@ def test_cli_usage_and_descriptors(capsys):
         assert e.value.code == 2
         capsys.readouterr()
     assert sd.build_ca(None, 32, 30, 513)["nsources"] == 4 and si.build_ca()["nsources"] == 2
+
+
+def test_cli_parse_long_options(tmp_path):
+    """`-i -o -m` as the reference scripts take them, plus the long options of SURVEY.md 5 (host logic only)"""
+    from deepconvsep_b200.examples import _common
+    o = _common.parse_cli(["-i", "a.wav", "-o", "out", "-m", "m.pkl"], "usage")
+    assert (o["inputfile"], o["outdir"], o["model"]) == ("a.wav", "out", "m.pkl")
+    assert o["frame_size"] is None and o["window"] is None and o["devices"] is None and o["batch_clips"] == 1
+    o = _common.parse_cli(["--ifile", "d", "--odir", "o", "--mfile", "m", "--frame-size", "2048", "--window", "blackmanharris",
+                           "--devices", "0,3", "--batch-clips", "4"], "usage")
+    assert o["frame_size"] == 2048 and o["window"] == "blackmanharris" and o["devices"] == [0, 3] and o["batch_clips"] == 4
+    import pytest
+    with pytest.raises(SystemExit):
+        _common.parse_cli(["-i", "a.wav"], "usage")            # -o / -m missing: usage + exit 2, like the reference
+    with pytest.raises(SystemExit):
+        _common.parse_cli(["--no-such-flag"], "usage")
