@@ -74,7 +74,8 @@ int upload(const std::vector<float>& h, float** d) {
 using namespace dcs;
 
 int64_t dcs_ctx::workspace_bytes() const {
-  size_t s = audio.cap + X.cap + mag.cap + S.cap + stems.cap + pcm_in.cap + pcm_out.cap;
+  size_t s = audio.cap + X.cap + mag.cap + S.cap + stems.cap + pcm_in.cap + pcm_out.cap + pcm_in2[0].cap + pcm_in2[1].cap +
+             pcm_out2[0].cap + pcm_out2[1].cap;
   for (const auto& b : net) s += b.cap;
   return (int64_t)s;
 }
@@ -140,6 +141,15 @@ int dcs_destroy(dcs_ctx* c) {
   c->audio.release(); c->X.release(); c->mag.release(); c->S.release(); c->stems.release();
   c->pcm_in.release(); c->pcm_out.release();
   for (auto& b : c->net) b.release();
+  for (int i = 0; i < 2; ++i) {
+    c->pcm_in2[i].release(); c->pcm_out2[i].release();
+    if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
+    if (c->ev_dec[i]) cudaEventDestroy(c->ev_dec[i]);
+    if (c->ev_enc[i]) cudaEventDestroy(c->ev_enc[i]);
+    if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]);
+  }
+  if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
+  if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
   delete c;
   return DCS_OK;
 }
@@ -668,6 +678,78 @@ int dcs_separate_pcm16_host(dcs_ctx* ctx, dcs_model* m, dcs_stft* p, const int16
   DCS_TRY(launch_pcm_encode(ctx, ctx->stems.as<float>(), L, m->nsrc, L, ctx->pcm_out.as<int16_t>(), L, st));
   DCS_CUDA(cudaMemcpy2DAsync(h_out, (size_t)out_stride * sizeof(int16_t), ctx->pcm_out.p, (size_t)L * sizeof(int16_t),
                              (size_t)L * sizeof(int16_t), m->nsrc, cudaMemcpyDeviceToHost, st));
+  DCS_CUDA(cudaStreamSynchronize(st));
+  return DCS_OK;
+}
+
+// Multi-clip scheduler: the clips of a batch run through ONE context as a three-stage pipeline -- H2D of clip i+1
+// (copy stream) | kernels of clip i (the caller's stream) | D2H of clip i-1 (second copy stream) -- with double-buffered
+// int16 staging on the device and events for the hand-overs.  The reference's only multi-clip driver starts a Python
+// process per file (examples/dsd100/separate_multiple.ipynb cell 3); per clip this is the wav contract of train_auto
+// (separate_dsd.py:275-287,307-309), exactly dcs_separate_pcm16_host.  Host buffers should be pinned.
+int dcs_separate_batch_pcm16_host(dcs_ctx* ctx, dcs_model* m, dcs_stft* p, int nclips, const int16_t* const* h_pcm,
+                                  const int64_t* num_samples, int channels, int downmix, float scale_factor, int overlap,
+                                  int patcher, int16_t* const* h_out, const int64_t* out_strides, void* stream) {
+  DCS_REQUIRE(ctx && m && p && h_pcm && num_samples && h_out && out_strides && nclips >= 0, "dcs_separate_batch_pcm16_host: bad argument");
+  DCS_REQUIRE(channels >= 1 && channels <= 8 && downmix >= 0 && downmix <= 2, "bad channels/downmix");
+  if (nclips == 0) return DCS_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  DCS_CUDA(cudaSetDevice(ctx->device));
+  int64_t Lmax = 0;
+  for (int i = 0; i < nclips; ++i) {
+    DCS_REQUIRE(h_pcm[i] && h_out[i] && num_samples[i] > 0 && out_strides[i] >= num_samples[i], "clip %d: bad buffer / length", i);
+    Lmax = std::max(Lmax, num_samples[i]);
+  }
+  if (!ctx->s_h2d) {
+    DCS_CUDA(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+    DCS_CUDA(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      DCS_CUDA(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
+      DCS_CUDA(cudaEventCreateWithFlags(&ctx->ev_dec[i], cudaEventDisableTiming));
+      DCS_CUDA(cudaEventCreateWithFlags(&ctx->ev_enc[i], cudaEventDisableTiming));
+      DCS_CUDA(cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming));
+    }
+  }
+  // every buffer at the size of the longest clip before the pipeline starts: a grow-only buffer that had to be
+  // re-allocated mid-batch would synchronise the stream
+  for (int b = 0; b < 2; ++b) {
+    DCS_TRY(ctx->pcm_in2[b].ensure((size_t)Lmax * channels * sizeof(int16_t), st));
+    DCS_TRY(ctx->pcm_out2[b].ensure((size_t)m->nsrc * Lmax * sizeof(int16_t), st));
+  }
+  DCS_TRY(ctx->audio.ensure((size_t)Lmax * sizeof(float), st));
+  DCS_TRY(ctx->stems.ensure((size_t)m->nsrc * Lmax * sizeof(float), st));
+  {
+    const int64_t T = dcs_num_frames(Lmax, p->hop), ldf = dcs_padded_bins(p->N);
+    DCS_TRY(ctx->X.ensure((size_t)T * ldf * sizeof(float2), st));
+    DCS_TRY(ctx->mag.ensure((size_t)T * ldf * sizeof(float), st));
+    DCS_TRY(ctx->S.ensure((size_t)m->nsrc * T * ldf * sizeof(float2), st));
+  }
+  // the copy streams start after whatever the caller queued on `st` (and after the memsets of fresh buffers)
+  DCS_CUDA(cudaEventRecord(ctx->ev_dec[0], st));
+  DCS_CUDA(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_dec[0], 0));
+  DCS_CUDA(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_dec[0], 0));
+  for (int i = 0; i < nclips; ++i) {
+    const int b = i & 1;
+    const int64_t L = num_samples[i];
+    // H2D of clip i: its staging buffer is free once the decode of clip i-2 has read it
+    if (i >= 2) DCS_CUDA(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_dec[b], 0));
+    DCS_CUDA(cudaMemcpyAsync(ctx->pcm_in2[b].p, h_pcm[i], (size_t)L * channels * sizeof(int16_t), cudaMemcpyHostToDevice, ctx->s_h2d));
+    DCS_CUDA(cudaEventRecord(ctx->ev_in[b], ctx->s_h2d));
+    // kernels of clip i
+    DCS_CUDA(cudaStreamWaitEvent(st, ctx->ev_in[b], 0));
+    DCS_TRY(launch_pcm_decode(ctx, ctx->pcm_in2[b].as<int16_t>(), L, channels, downmix, ctx->audio.as<float>(), st));
+    DCS_CUDA(cudaEventRecord(ctx->ev_dec[b], st));
+    DCS_TRY(dcs_separate_audio(ctx, m, p, ctx->audio.as<float>(), L, scale_factor, overlap, patcher, ctx->stems.as<float>(), L, stream));
+    if (i >= 2) DCS_CUDA(cudaStreamWaitEvent(st, ctx->ev_out[b], 0));     // D2H of clip i-2 has drained the output staging
+    DCS_TRY(launch_pcm_encode(ctx, ctx->stems.as<float>(), L, m->nsrc, L, ctx->pcm_out2[b].as<int16_t>(), L, st));
+    DCS_CUDA(cudaEventRecord(ctx->ev_enc[b], st));
+    // D2H of clip i
+    DCS_CUDA(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_enc[b], 0));
+    DCS_CUDA(cudaMemcpy2DAsync(h_out[i], (size_t)out_strides[i] * sizeof(int16_t), ctx->pcm_out2[b].p, (size_t)L * sizeof(int16_t),
+                               (size_t)L * sizeof(int16_t), m->nsrc, cudaMemcpyDeviceToHost, ctx->s_d2h));
+    DCS_CUDA(cudaEventRecord(ctx->ev_out[b], ctx->s_d2h));
+  }
+  DCS_CUDA(cudaStreamSynchronize(ctx->s_d2h));
   DCS_CUDA(cudaStreamSynchronize(st));
   return DCS_OK;
 }

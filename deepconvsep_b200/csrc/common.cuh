@@ -83,6 +83,10 @@ struct dcs_ctx {
   std::vector<dcs_prof_rec> prof;
   // workspace of one in-flight pipeline
   dcs::DevBuf audio, X, mag, S, stems, pcm_in, pcm_out;
+  // multi-clip scheduler (dcs_separate_batch_pcm16_host): copy streams, double-buffered staging, hand-over events
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_dec[2] = {nullptr, nullptr}, ev_enc[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+  dcs::DevBuf pcm_in2[2], pcm_out2[2];
   dcs::DevBuf net[12];
   uint64_t net_sig[12] = {0};   // layout signature of what each net[] buffer currently holds
   float2* tap = nullptr;        // dcs_set_spectrum_tap: copy of the masked spectra the iSTFT consumed

@@ -269,6 +269,28 @@ class Separator(object):
                                                     self.patcher, out.ctypes.data, L, _stream_ptr(None, self.ctx.device)))
         return out
 
+    def separate_pcm16_batch(self, clips, downmix=1, outs=None):
+        """Several clips through the context's multi-clip scheduler (dcs_separate_batch_pcm16_host): H2D of clip i+1,
+        the kernels of clip i and D2H of clip i-1 overlap.  clips: list of int16 arrays [L] or [L, channels] (same
+        channel count; pinned for real overlap) -> list of int16 [nsrc, L]."""
+        ps = [np.ascontiguousarray(c, dtype=np.int16) for c in clips]
+        n = len(ps)
+        if n == 0:
+            return []
+        ch = 1 if ps[0].ndim == 1 else ps[0].shape[1]
+        assert all((1 if p_.ndim == 1 else p_.shape[1]) == ch for p_ in ps), "all clips must have the same channel count"
+        Ls = np.array([p_.shape[0] for p_ in ps], dtype=np.int64)
+        if outs is None:
+            outs = [np.empty((self.nsrc, int(L)), dtype=np.int16) for L in Ls]
+        assert all(o.dtype == np.int16 and o.shape == (self.nsrc, int(L)) and o.flags.c_contiguous for o, L in zip(outs, Ls))
+        pin = (C.c_void_p * n)(*[p_.ctypes.data for p_ in ps])
+        pout = (C.c_void_p * n)(*[o.ctypes.data for o in outs])
+        _lib.check(self.lib.dcs_separate_batch_pcm16_host(self.ctx.handle, self.model.handle, self.stft.handle, n, pin,
+                                                          Ls.ctypes.data, ch, int(downmix if ch > 1 else 0), self.scale_factor,
+                                                          self.overlap, self.patcher, pout, Ls.ctypes.data,
+                                                          _stream_ptr(None, self.ctx.device)))
+        return outs
+
     # ---- device buffers (torch tensors) ----
     def separate_device(self, audio, out=None, stream=None):
         """audio: torch float32 cuda [L] -> torch float32 cuda [nsrc, L]; asynchronous."""

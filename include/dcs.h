@@ -203,6 +203,17 @@ int dcs_separate_pcm16_host(dcs_ctx* ctx, dcs_model* model, dcs_stft* plan, cons
                             int overlap, int patcher, int16_t* h_out, int64_t out_stride,
                             void* stream);
 
+/* Multi-clip scheduler: `nclips` clips through one context as a pipeline -- H2D of clip i+1 | kernels of clip i | D2H of
+ * clip i-1 -- on two internal copy streams and `stream`, with double-buffered int16 staging on the device.  Replaces the
+ * reference's process-per-file loop (examples/dsd100/separate_multiple.ipynb cell 3); per clip the contract is that of
+ * dcs_separate_pcm16_host.  h_pcm[i]: int16[num_samples[i]][channels] (pinned for real overlap), h_out[i]:
+ * int16[nsrc][out_strides[i]].  Order the clips longest first if their lengths differ much (grow-only workspace).
+ * Synchronises before returning. */
+int dcs_separate_batch_pcm16_host(dcs_ctx* ctx, dcs_model* model, dcs_stft* plan, int nclips,
+                                  const int16_t* const* h_pcm, const int64_t* num_samples, int channels, int downmix,
+                                  float scale_factor, int overlap, int patcher, int16_t* const* h_out,
+                                  const int64_t* out_strides, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -146,3 +146,24 @@ def test_cli_long_options_directory_of_clips(tmp_path):
             _, a = scipy.io.wavfile.read(str(out1 / (src + ".wav")))
             _, b = scipy.io.wavfile.read(str(out2 / n.replace(".wav", "_" + src + ".wav")))
             assert np.array_equal(a, b), (n, src)
+
+
+def test_batch_scheduler_matches_per_clip_calls():
+    """dcs_separate_batch_pcm16_host (H2D | kernels | D2H pipelined over the clips of a batch, double-buffered staging)
+    gives the bits of dcs_separate_pcm16_host clip by clip -- different lengths, stereo input, called twice."""
+    from deepconvsep_b200.engine import Separator
+    params = nets.make_synthetic_params("dsd", 513, seed=12)
+    sep = Separator(params, frame_size=1024, hop=512, window="hanning", overlap=25)
+    rng = np.random.default_rng(1)
+    clips = []
+    for k, secs in enumerate((2.0, 3.1, 1.2, 2.6, 0.3)):
+        mix, _ = pipeline.synth_mixture(secs, 60 + k)
+        clips.append(np.stack([np.round(mix * 30000), np.round((0.7 * mix + 0.01 * rng.standard_normal(mix.size)) * 30000)],
+                              axis=1).astype(np.int16))
+    want = [sep.separate_pcm16(c) for c in clips]
+    for _ in range(2):
+        got = sep.separate_pcm16_batch(clips)
+        assert len(got) == len(want)
+        for g, w in zip(got, want):
+            assert g.shape == w.shape and np.array_equal(g, w)
+    assert sep.separate_pcm16_batch([]) == []
