@@ -48,7 +48,7 @@ def build(force=False, verbose=False):
         fail |= p.returncode != 0
     if fail:
         raise RuntimeError("nvcc failed")
-    cmd = [_nvcc(), "-shared", "-cudart", "static", "-o", LIB] + objs
+    cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static", "-o", LIB] + objs
     subprocess.check_call(cmd)
     return LIB
 
