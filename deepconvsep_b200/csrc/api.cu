@@ -687,43 +687,11 @@ int dcs_separate_pcm16_host(dcs_ctx* ctx, dcs_model* m, dcs_stft* p, const int16
 // int16 staging on the device and events for the hand-overs.  The reference's only multi-clip driver starts a Python
 // process per file (examples/dsd100/separate_multiple.ipynb cell 3); per clip this is the wav contract of train_auto
 // (separate_dsd.py:275-287,307-309), exactly dcs_separate_pcm16_host.  Host buffers should be pinned.
-int dcs_separate_batch_pcm16_host(dcs_ctx* ctx, dcs_model* m, dcs_stft* p, int nclips, const int16_t* const* h_pcm,
-                                  const int64_t* num_samples, int channels, int downmix, float scale_factor, int overlap,
-                                  int patcher, int16_t* const* h_out, const int64_t* out_strides, void* stream) {
-  DCS_REQUIRE(ctx && m && p && h_pcm && num_samples && h_out && out_strides && nclips >= 0, "dcs_separate_batch_pcm16_host: bad argument");
-  DCS_REQUIRE(channels >= 1 && channels <= 8 && downmix >= 0 && downmix <= 2, "bad channels/downmix");
-  if (nclips == 0) return DCS_OK;
-  cudaStream_t st = (cudaStream_t)stream;
-  DCS_CUDA(cudaSetDevice(ctx->device));
-  int64_t Lmax = 0;
-  for (int i = 0; i < nclips; ++i) {
-    DCS_REQUIRE(h_pcm[i] && h_out[i] && num_samples[i] > 0 && out_strides[i] >= num_samples[i], "clip %d: bad buffer / length", i);
-    Lmax = std::max(Lmax, num_samples[i]);
-  }
-  if (!ctx->s_h2d) {
-    DCS_CUDA(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
-    DCS_CUDA(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
-      DCS_CUDA(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
-      DCS_CUDA(cudaEventCreateWithFlags(&ctx->ev_dec[i], cudaEventDisableTiming));
-      DCS_CUDA(cudaEventCreateWithFlags(&ctx->ev_enc[i], cudaEventDisableTiming));
-      DCS_CUDA(cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming));
-    }
-  }
-  // every buffer at the size of the longest clip before the pipeline starts: a grow-only buffer that had to be
-  // re-allocated mid-batch would synchronise the stream
-  for (int b = 0; b < 2; ++b) {
-    DCS_TRY(ctx->pcm_in2[b].ensure((size_t)Lmax * channels * sizeof(int16_t), st));
-    DCS_TRY(ctx->pcm_out2[b].ensure((size_t)m->nsrc * Lmax * sizeof(int16_t), st));
-  }
-  DCS_TRY(ctx->audio.ensure((size_t)Lmax * sizeof(float), st));
-  DCS_TRY(ctx->stems.ensure((size_t)m->nsrc * Lmax * sizeof(float), st));
-  {
-    const int64_t T = dcs_num_frames(Lmax, p->hop), ldf = dcs_padded_bins(p->N);
-    DCS_TRY(ctx->X.ensure((size_t)T * ldf * sizeof(float2), st));
-    DCS_TRY(ctx->mag.ensure((size_t)T * ldf * sizeof(float), st));
-    DCS_TRY(ctx->S.ensure((size_t)m->nsrc * T * ldf * sizeof(float2), st));
-  }
+// the pipelined loop of dcs_separate_batch_pcm16_host; on any failure the caller drains the copy streams before it
+// returns, because the copies in flight read and write the user's host buffers
+static int batch_pipeline(dcs_ctx* ctx, dcs_model* m, dcs_stft* p, int nclips, const int16_t* const* h_pcm,
+                          const int64_t* num_samples, int channels, int downmix, float scale_factor, int overlap,
+                          int patcher, int16_t* const* h_out, const int64_t* out_strides, cudaStream_t st) {
   // the copy streams start after whatever the caller queued on `st` (and after the memsets of fresh buffers)
   DCS_CUDA(cudaEventRecord(ctx->ev_dec[0], st));
   DCS_CUDA(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_dec[0], 0));
@@ -739,7 +707,7 @@ int dcs_separate_batch_pcm16_host(dcs_ctx* ctx, dcs_model* m, dcs_stft* p, int n
     DCS_CUDA(cudaStreamWaitEvent(st, ctx->ev_in[b], 0));
     DCS_TRY(launch_pcm_decode(ctx, ctx->pcm_in2[b].as<int16_t>(), L, channels, downmix, ctx->audio.as<float>(), st));
     DCS_CUDA(cudaEventRecord(ctx->ev_dec[b], st));
-    DCS_TRY(dcs_separate_audio(ctx, m, p, ctx->audio.as<float>(), L, scale_factor, overlap, patcher, ctx->stems.as<float>(), L, stream));
+    DCS_TRY(dcs_separate_audio(ctx, m, p, ctx->audio.as<float>(), L, scale_factor, overlap, patcher, ctx->stems.as<float>(), L, (void*)st));
     if (i >= 2) DCS_CUDA(cudaStreamWaitEvent(st, ctx->ev_out[b], 0));     // D2H of clip i-2 has drained the output staging
     DCS_TRY(launch_pcm_encode(ctx, ctx->stems.as<float>(), L, m->nsrc, L, ctx->pcm_out2[b].as<int16_t>(), L, st));
     DCS_CUDA(cudaEventRecord(ctx->ev_enc[b], st));
@@ -749,8 +717,53 @@ int dcs_separate_batch_pcm16_host(dcs_ctx* ctx, dcs_model* m, dcs_stft* p, int n
                                (size_t)L * sizeof(int16_t), m->nsrc, cudaMemcpyDeviceToHost, ctx->s_d2h));
     DCS_CUDA(cudaEventRecord(ctx->ev_out[b], ctx->s_d2h));
   }
-  DCS_CUDA(cudaStreamSynchronize(ctx->s_d2h));
-  DCS_CUDA(cudaStreamSynchronize(st));
+  return DCS_OK;
+}
+
+int dcs_separate_batch_pcm16_host(dcs_ctx* ctx, dcs_model* m, dcs_stft* p, int nclips, const int16_t* const* h_pcm,
+                                  const int64_t* num_samples, int channels, int downmix, float scale_factor, int overlap,
+                                  int patcher, int16_t* const* h_out, const int64_t* out_strides, void* stream) {
+  DCS_REQUIRE(ctx && m && p && h_pcm && num_samples && h_out && out_strides && nclips >= 0, "dcs_separate_batch_pcm16_host: bad argument");
+  DCS_REQUIRE(channels >= 1 && channels <= 8 && downmix >= 0 && downmix <= 2, "bad channels/downmix");
+  if (nclips == 0) return DCS_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  DCS_CUDA(cudaSetDevice(ctx->device));
+  int64_t Lmax = 0;
+  for (int i = 0; i < nclips; ++i) {
+    DCS_REQUIRE(h_pcm[i] && h_out[i] && num_samples[i] > 0 && out_strides[i] >= num_samples[i], "clip %d: bad buffer / length", i);
+    Lmax = std::max(Lmax, num_samples[i]);
+  }
+  // each resource on its own: a call that failed half-way through this block must not leave later calls with null handles
+  if (!ctx->s_h2d) DCS_CUDA(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+  if (!ctx->s_d2h) DCS_CUDA(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    if (!ctx->ev_in[i]) DCS_CUDA(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
+    if (!ctx->ev_dec[i]) DCS_CUDA(cudaEventCreateWithFlags(&ctx->ev_dec[i], cudaEventDisableTiming));
+    if (!ctx->ev_enc[i]) DCS_CUDA(cudaEventCreateWithFlags(&ctx->ev_enc[i], cudaEventDisableTiming));
+    if (!ctx->ev_out[i]) DCS_CUDA(cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming));
+  }
+  // every buffer at the size of the longest clip before the pipeline starts: a grow-only buffer that had to be
+  // re-allocated mid-batch would synchronise the stream
+  for (int b = 0; b < 2; ++b) {
+    DCS_TRY(ctx->pcm_in2[b].ensure((size_t)Lmax * channels * sizeof(int16_t), st));
+    DCS_TRY(ctx->pcm_out2[b].ensure((size_t)m->nsrc * Lmax * sizeof(int16_t), st));
+  }
+  DCS_TRY(ctx->audio.ensure((size_t)Lmax * sizeof(float), st));
+  DCS_TRY(ctx->stems.ensure((size_t)m->nsrc * Lmax * sizeof(float), st));
+  {
+    const int64_t T = dcs_num_frames(Lmax, p->hop), ldf = dcs_padded_bins(p->N);
+    DCS_TRY(ctx->X.ensure((size_t)T * ldf * sizeof(float2), st));
+    DCS_TRY(ctx->mag.ensure((size_t)T * ldf * sizeof(float), st));
+    DCS_TRY(ctx->S.ensure((size_t)m->nsrc * T * ldf * sizeof(float2), st));
+  }
+  const int rc = batch_pipeline(ctx, m, p, nclips, h_pcm, num_samples, channels, downmix, scale_factor, overlap, patcher,
+                                h_out, out_strides, st);
+  // drain everything, success or not, before the host buffers go back to the caller
+  const cudaError_t e0 = cudaStreamSynchronize(ctx->s_h2d), e1 = cudaStreamSynchronize(ctx->s_d2h), e2 = cudaStreamSynchronize(st);
+  if (rc != DCS_OK) return rc;
+  DCS_CUDA(e0);
+  DCS_CUDA(e1);
+  DCS_CUDA(e2);
   return DCS_OK;
 }
 

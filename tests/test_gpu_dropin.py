@@ -167,3 +167,9 @@ def test_batch_scheduler_matches_per_clip_calls():
         for g, w in zip(got, want):
             assert g.shape == w.shape and np.array_equal(g, w)
     assert sep.separate_pcm16_batch([]) == []
+    # a bad clip is refused before anything is queued, and the context keeps working
+    from deepconvsep_b200._lib import DcsError
+    with pytest.raises(DcsError, match="clip 1"):
+        sep.separate_pcm16_batch([clips[0], np.zeros((0, 2), dtype=np.int16)])
+    again = sep.separate_pcm16_batch(clips[:2])
+    assert np.array_equal(again[0], want[0]) and np.array_equal(again[1], want[1])
