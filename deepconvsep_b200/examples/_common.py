@@ -1,6 +1,7 @@
 """Shared driver of the stand-alone separation scripts: `train_auto` of
 examples/dsd100/separate_dsd.py:239-313 (and its iKala / Bach10 siblings) on the CUDA pipeline."""
 import os
+import threading
 import numpy as np
 import scipy.io.wavfile
 
@@ -8,19 +9,21 @@ from ..engine import Separator, get_window
 from ..models import load_model, FAMILY_DEFAULTS
 
 _cache = {}
+_cache_lock = threading.Lock()       # run_many's worker threads share the cache
 
 
 def get_separator(model, arch, frame_size, hop, window, scale_factor, time_context, overlap, feat_size, device=0, slot=0):
     key = (os.path.abspath(model), os.path.getmtime(model), arch, frame_size, hop, str(window), scale_factor,
            time_context, overlap)
-    if _cache.get("key") != key:
-        _cache.clear()   # one resident model at a time (Bach10 weights are 856 MB), per (device, slot)
-        _cache["key"] = key
-    if (device, slot) not in _cache:
-        _cache[(device, slot)] = Separator(load_model(model), arch=arch, frame_size=frame_size, hop=hop, window=window,
-                                           scale_factor=scale_factor, time_context=time_context, overlap=overlap,
-                                           patcher="standalone", feat_size=feat_size, device=device)
-    return _cache[(device, slot)]
+    with _cache_lock:
+        if _cache.get("key") != key:
+            _cache.clear()   # one resident model at a time (Bach10 weights are 856 MB), per (device, slot)
+            _cache["key"] = key
+        if (device, slot) not in _cache:
+            _cache[(device, slot)] = Separator(load_model(model), arch=arch, frame_size=frame_size, hop=hop, window=window,
+                                               scale_factor=scale_factor, time_context=time_context, overlap=overlap,
+                                               patcher="standalone", feat_size=feat_size, device=device)
+        return _cache[(device, slot)]
 
 
 def decode(audioObj, family):
@@ -51,11 +54,22 @@ def run(family, filein, outdir, model, scale_factor, time_context, overlap, batc
         print("Sample rate is not 44100")        # separate_dsd.py:313
         return None
     arch = None if family in ("ikala",) else family
-    sep = get_separator(model, arch, frame_size, hop, d["window"], scale_factor, time_context, overlap, input_size,
-                        device=device, slot=slot)
-    if audioObj.dtype == np.int16 and family != "ikala":
+    if isinstance(device, (list, tuple)):
+        # one recording over several GPUs: hop- and patch-aligned segments with margins, one host thread per device,
+        # the stitched stems are those of the whole-clip call (deepconvsep_b200.longclip)
+        from .. import longclip
+        seps = [get_separator(model, arch, frame_size, hop, d["window"], scale_factor, time_context, overlap, input_size,
+                              device=dev, slot=slot) for dev in device]
+        sep = seps[0]
+        stems = longclip.separate_long(seps, decode(audioObj, family))
+        stems16 = (stems.astype(np.float64) * np.iinfo(np.int16).max).astype('int16')
+    elif audioObj.dtype == np.int16 and family != "ikala":
+        sep = get_separator(model, arch, frame_size, hop, d["window"], scale_factor, time_context, overlap, input_size,
+                            device=device, slot=slot)
         stems16 = sep.separate_pcm16(audioObj, downmix=1)          # decode/downmix/encode on the GPU
     else:
+        sep = get_separator(model, arch, frame_size, hop, d["window"], scale_factor, time_context, overlap, input_size,
+                            device=device, slot=slot)
         audio = decode(audioObj, family)
         stems = sep.separate(audio)
         stems16 = (stems.astype(np.float64) * np.iinfo(np.int16).max).astype('int16')
@@ -71,7 +85,8 @@ def run(family, filein, outdir, model, scale_factor, time_context, overlap, batc
 # ---- command line shared by the separate_*.py scripts ------------------------------------------------------
 LONG_OPTS = ["ifile=", "odir=", "mfile=", "frame-size=", "window=", "devices=", "batch-clips="]
 EXTRA_USAGE = ("  optional: --frame-size N (STFT frame, feat_size = N/2+1)  --window hanning|blackmanharris|sinebell\n"
-               "            --devices 0,1,...  --batch-clips K (clips in flight per device); with these, -i may be a directory of wavs")
+               "            --devices 0,1,...  --batch-clips K (clips in flight per device); with these, -i may be a directory of wavs\n"
+               "            (one wav and several devices: the recording itself is cut into segments over the devices)")
 
 
 def parse_cli(argv, usage):
@@ -122,7 +137,11 @@ def cli_main(argv, usage, train_auto_default, run_one):
         files = sorted(os.path.join(o["inputfile"], f) for f in os.listdir(o["inputfile"]) if f.lower().endswith(".wav"))
     else:
         files = [o["inputfile"]]
-    return run_many(files, o["outdir"], o["model"], o["frame_size"], o["window"], o["devices"] or [0], o["batch_clips"], run_one)
+    devices = o["devices"] or [0]
+    if len(files) == 1 and len(devices) > 1:
+        # a single recording and several GPUs: split the recording (run() with a device list), not the file list
+        return [run_one(files[0], o["outdir"], o["model"], o["frame_size"], o["window"], devices, 0, False)]
+    return run_many(files, o["outdir"], o["model"], o["frame_size"], o["window"], devices, o["batch_clips"], run_one)
 
 
 def run_many(files, outdir, model, frame_size, window, devices, batch_clips, run_one):

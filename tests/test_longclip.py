@@ -129,3 +129,40 @@ def test_two_rank_gloo_long_clip():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert err <= 1e-13
+
+
+def test_cli_splits_one_recording_over_the_listed_devices(tmp_path, monkeypatch):
+    """`separate_dsd.py -i one.wav --devices 0,1`: the recording (not a file list) is cut over the devices; with a
+    stand-in for the CUDA Separator that scales its input per source, the wavs are those of a whole-clip call."""
+    import scipy.io.wavfile
+    from types import SimpleNamespace
+    from deepconvsep_b200.examples import _common
+    from deepconvsep_b200.examples.dsd100 import separate_dsd
+
+    calls = []
+
+    class FakeSeparator(object):
+        def __init__(self, device):
+            self.device = device
+            self.model = SimpleNamespace(arch="dsd", tc=30)
+            self.frame_size, self.hop, self.overlap = 1024, 512, 25
+            self.sources = ["vocals", "bass", "drums", "other"]
+
+        def separate(self, sub):
+            calls.append((self.device, len(sub)))
+            return np.stack([np.asarray(sub, dtype=np.float32) * g for g in (0.5, 0.25, 0.125, 0.0625)])
+
+    monkeypatch.setattr(_common, "get_separator", lambda *a, device=0, slot=0, **k: FakeSeparator(device))
+    rng = np.random.default_rng(0)
+    pcm = (rng.uniform(-0.5, 0.5, size=(44100 * 6, 2)) * 32767).astype(np.int16)
+    wav = tmp_path / "one.wav"
+    scipy.io.wavfile.write(str(wav), 44100, pcm)
+    out = tmp_path / "out"
+    out.mkdir()
+    separate_dsd.main(["-i", str(wav), "-o", str(out), "-m", "unused.pkl", "--devices", "0,1"])
+    assert sorted(d for d, _ in calls) == [0, 1] and all(n < len(pcm) for _, n in calls)
+    mono = (pcm[:, 0] / 32767.0 + pcm[:, 1] / 32767.0) / 2
+    for name, g in zip(("vocals", "bass", "drums", "other"), (0.5, 0.25, 0.125, 0.0625)):
+        sr, got = scipy.io.wavfile.read(str(out / (name + ".wav")))
+        want = ((mono.astype(np.float32) * np.float32(g)).astype(np.float64) * 32767).astype(np.int16)
+        assert sr == 44100 and np.array_equal(got, want)
