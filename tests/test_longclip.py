@@ -166,3 +166,51 @@ def test_cli_splits_one_recording_over_the_listed_devices(tmp_path, monkeypatch)
         sr, got = scipy.io.wavfile.read(str(out / (name + ".wav")))
         want = ((mono.astype(np.float32) * np.float32(g)).astype(np.float64) * 32767).astype(np.int16)
         assert sr == 44100 and np.array_equal(got, want)
+
+
+def _toy_engine(N, H, tc, ov, patcher):
+    """The pipeline's time structure with a toy network: every output frame of a patch depends on ALL frames of the
+    patch (so one contaminated frame spoils the whole patch), two sources, the real patchers / cross-fade / STFTs."""
+    from oracle import patch
+    gen = patch.generate_overlapadd if patcher == "standalone" else patch.generate_overlapadd_util
+
+    def fn(sub, filt):
+        sub = np.asarray(sub, dtype=np.float64)
+        mag, ph = dsp.compute_file(sub, phase=True, frameSize=N, hopSize=H, window=np.hanning)
+        batches, n = gen(mag, input_size=mag.shape[-1], time_context=tc, overlap=ov, batch_size=4)
+        if n == 0:
+            mm = np.zeros((2, len(ph), mag.shape[-1]))
+        else:
+            g = 1.0 / (1.0 + np.exp(-20.0 * batches.mean(axis=(2, 3, 4), keepdims=True)))      # one number per patch
+            out = np.stack([batches * g, batches * (1.0 - g)], axis=1)                        # [nb, 2, B, 1, tc, F]
+            mm = patch.overlapadd_multi(out, batches, n, overlap=ov)
+        stems = []
+        for s in range(2):
+            m = mm[s, :len(ph)]
+            if m.shape[0] < len(ph):
+                m = np.concatenate([m, np.zeros((len(ph) - m.shape[0], m.shape[1]))])
+            stems.append(dsp.compute_inverse(m, ph, frameSize=N, hopSize=H, window=np.hanning)[:len(sub)])
+        return np.stack(stems)
+    return fn
+
+
+def test_margins_are_exact_for_many_geometries():
+    """frame sizes / hops / contexts / overlaps the reference never uses (N/2 not a multiple of the hop, step 1,
+    step = time_context - 1, overlap 1 ...), both patchers, clip lengths on and off the grids"""
+    rng = np.random.default_rng(7)
+    cases = 0
+    for N, H in ((64, 16), (64, 32), (96, 20), (128, 8), (32, 32)):
+        for tc, ov in ((6, 4), (6, 5), (5, 1), (8, 3), (30, 25)):
+            for patcher in ("standalone", "util"):
+                left, right = longclip.margins(N, H, tc, ov)
+                L = int(3.2 * 2 * (left + right)) + int(rng.integers(0, 3 * H))
+                x = rng.standard_normal(L) * np.hanning(L) + 0.1 * np.sin(np.arange(L) * 0.05)
+                fn = _toy_engine(N, H, tc, ov, patcher)
+                whole = fn(x, None)
+                segs = longclip.plan_segments(L, 3, N, H, tc, ov)
+                assert len(segs) == 3, (N, H, tc, ov, L)
+                got = longclip.separate_long(fn, x, parts=3, geometry=(N, H, tc, ov))
+                err = np.abs(got - whole).max() / np.abs(whole).max()
+                assert err <= 1e-12, (N, H, tc, ov, patcher, err)
+                cases += 1
+    assert cases == 50
