@@ -22,6 +22,10 @@ Parity pinning status
   here (Python 3.12, no network), and the reference ships no tests, golden vectors or
   trained weights.  The restatement follows Lasagne's documented layer semantics
    and is cross-checked in `tests/test_oracle_nets.py` against an
-  independent torch-autograd formulation (InverseLayer == gradient wrt the layer input).
+  independent torch-autograd formulation (InverseLayer == gradient wrt the layer input);
+  `tests/test_oracle_layer_pins.py` holds each layer to a third-party implementation of the
+  published definition it stands for (scipy.signal.convolve2d / correlate2d, the adjoint
+  identity, torch max_pool2d / max_unpool2d, the DSD net rebuilt from torch library layers).
+  That narrows what "unpinned" leaves open to Lasagne deviating from its own documentation.
 """
 from . import dsp, patch, nets, pipeline  # noqa: F401
