@@ -111,3 +111,47 @@ def test_dense_layer_flattening_and_whole_net_against_library_layers():
         decs.append(d1)
     merged = torch.cat([decs[i] for i in a["dec_of_out"]], dim=1) + p[-1][None, :, None, None]
     assert np.abs(merged.numpy() - want_pre).max() <= 1e-12 * np.abs(want_pre).max()
+
+
+def _library_net(params, x, arch):
+    """Any of the single-stream nets from torch's library layers: conv2d (flipped filters, stride), max_pool2d with
+    indices, linear, conv_transpose2d (tied flipped filters, stride, output_padding up to the input width),
+    max_unpool2d.  Pre-rectify output, like nets.predict(..., return_pre=True)."""
+    a = nets.ARCHS[arch]
+    B, nch, tc, F = x.shape
+    d = nets.arch_dims(arch, F, tc)
+    p = [torch.tensor(np.asarray(v, dtype=np.float64)) for v in params]
+    xt = torch.tensor(np.asarray(x, dtype=np.float64))
+    flip = lambda w: torch.flip(w, dims=(2, 3))
+    s1 = (d["sh1"], d["sw1"])
+    h1 = Fn.conv2d(xt, flip(p[0]), stride=s1) + (p[1] + p[2])[None, :, None, None]
+    if a["pool"]:
+        hp, idx = Fn.max_pool2d(h1, (1, a["pool"]), return_indices=True)
+    else:
+        hp = h1
+    h2 = Fn.conv2d(hp, flip(p[3])) + (p[4] + p[5])[None, :, None, None]
+    z = torch.relu(h2.reshape(B, -1) @ p[6] + p[7])
+    decs = []
+    for s in range(d["ndec"]):
+        r = torch.relu(z @ p[8 + 2 * s] + p[9 + 2 * s]).reshape(h2.shape)
+        g = Fn.conv_transpose2d(r, flip(p[3]))
+        if a["pool"]:
+            g = Fn.max_unpool2d(g, idx, (1, a["pool"]), output_size=h1.shape[2:])
+        covered = (h1.shape[3] - 1) * s1[1] + p[0].shape[3]
+        out = Fn.conv_transpose2d(g, flip(p[0]), stride=s1)
+        assert out.shape[3] == covered <= F
+        decs.append(Fn.pad(out, (0, F - covered)))                # bins no stride window covers stay 0
+    merged = torch.cat([decs[i] for i in a["dec_of_out"]], dim=1) + p[-1][None, :, None, None]
+    return merged.numpy()
+
+
+def test_strided_and_pooled_nets_against_library_layers():
+    rng = np.random.default_rng(5)
+    for arch, F in (("ikala", 513), ("ikala_nopool", 257), ("bach10", 130), ("bach10_score", 131)):
+        params = nets.make_synthetic_params(arch, F, seed=6, dtype=np.float64, out_bias=0.05)
+        nch = nets.ARCHS[arch]["nch"]
+        x = np.abs(rng.standard_normal((2, nch, 30, F))) * 0.3        # continuous random input: no ties in any window
+        want = nets.predict(params, x, arch, return_pre=True)
+        got = _library_net(params, x, arch)
+        assert got.shape == want.shape
+        assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max(), arch
