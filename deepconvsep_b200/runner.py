@@ -79,7 +79,8 @@ def separate_dataset(family, testdir, outdir, model, scale_factor=0.3, time_cont
     jobs = list_jobs(family, testdir, outdir)
     sizes = [os.path.getsize(j[0]) for j in jobs]
     seconds = 0.0
-    for idx in shard_clips(sizes, world_size, rank):
+    # longest first: the workspace buffers only grow, so the first song sizes them once for the whole shard
+    for idx in sorted(shard_clips(sizes, world_size, rank), key=lambda i: (-sizes[i], i)):
         wav, outs = jobs[idx]
         audioObj, sampleRate, bitrate = util.readAudioScipy(wav)
         assert sampleRate == 44100, "Sample rate needs to be 44100"
