@@ -208,7 +208,9 @@ int dcs_separate_pcm16_host(dcs_ctx* ctx, dcs_model* model, dcs_stft* plan, cons
  * reference's process-per-file loop (examples/dsd100/separate_multiple.ipynb cell 3); per clip the contract is that of
  * dcs_separate_pcm16_host.  h_pcm[i]: int16[num_samples[i]][channels] (pinned for real overlap), h_out[i]:
  * int16[nsrc][out_strides[i]].  Order the clips longest first if their lengths differ much (grow-only workspace).
- * Synchronises before returning. */
+ * Synchronises before returning -- also when it returns an error: every copy in flight has drained, so the host
+ * buffers are the caller's again (outputs of clips after the failure are undefined).  Arguments are validated
+ * before anything is queued (DCS_EINVAL names the offending clip). */
 int dcs_separate_batch_pcm16_host(dcs_ctx* ctx, dcs_model* model, dcs_stft* plan, int nclips,
                                   const int16_t* const* h_pcm, const int64_t* num_samples, int channels, int downmix,
                                   float scale_factor, int overlap, int patcher, int16_t* const* h_out,
