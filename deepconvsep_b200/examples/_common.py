@@ -5,7 +5,7 @@ import threading
 import numpy as np
 import scipy.io.wavfile
 
-from ..engine import Separator, get_window
+from ..engine import Separator
 from ..models import load_model, FAMILY_DEFAULTS
 
 _cache = {}

@@ -3,7 +3,6 @@
     python -m deepconvsep_b200.examples.bach10.separate_bach10 -i <inputfile> -o <outputdir> -m <path_to_model.pkl>
 """
 import sys
-import numpy as np
 from scipy.signal.windows import blackmanharris  # the reference imports scipy.signal.blackmanharris (:4)
 
 from ...models import load_model                       # noqa: F401

@@ -15,7 +15,6 @@ import sys
 import getopt
 import numpy as np
 import scipy.io.wavfile
-from scipy.signal.windows import blackmanharris
 
 from ...models import load_model                       # noqa: F401
 from ...transform import sinebell, stft_norm, istft_norm, transformFFT  # noqa: F401

@@ -24,7 +24,6 @@ import os
 
 import numpy as np
 
-from oracle import dsp
 
 TOL = 1e-4
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -3,7 +3,6 @@ reduce the statistics exactly like bench.py does under torchrun."""
 import os
 import socket
 import numpy as np
-import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 

@@ -1,10 +1,9 @@
 """Quick device-side timing of the DSD100 pipeline (development aid, not the bench)."""
-import sys, os, time
+import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 from deepconvsep_b200.engine import Separator
-from deepconvsep_b200 import _lib
 
 def synth_params(F, seed=0):
     rng = np.random.default_rng(seed)
