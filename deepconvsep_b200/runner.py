@@ -69,6 +69,17 @@ def list_jobs(family, testdir, outdir):
     return jobs
 
 
+def _num_samples(path):
+    """Samples per channel from the wav header (memory-mapped, nothing is read); the shard balance and the
+    longest-first order go by duration, not by bytes (a 24/32-bit song is not longer than a 16-bit one)."""
+    import scipy.io.wavfile
+    try:
+        _, a = scipy.io.wavfile.read(path, mmap=True)
+        return int(a.shape[0])
+    except Exception:  # noqa: BLE001  (unreadable header: fall back to the byte count, the read itself will report)
+        return int(os.path.getsize(path))
+
+
 def separate_dataset(family, testdir, outdir, model, scale_factor=0.3, time_context=30, rank=0, world_size=1, device=0,
                      **overrides):
     cfg = dict(TRAINER[family], **overrides)
@@ -77,7 +88,7 @@ def separate_dataset(family, testdir, outdir, model, scale_factor=0.3, time_cont
                     window=cfg["window"], scale_factor=scale_factor, time_context=time_context, overlap=cfg["overlap"],
                     patcher="util", device=device, feat_size=cfg["frameSize"] // 2 + 1)
     jobs = list_jobs(family, testdir, outdir)
-    sizes = [os.path.getsize(j[0]) for j in jobs]
+    sizes = [_num_samples(j[0]) for j in jobs]
     seconds = 0.0
     # longest first: the workspace buffers only grow, so the first song sizes them once for the whole shard
     for idx in sorted(shard_clips(sizes, world_size, rank), key=lambda i: (-sizes[i], i)):
