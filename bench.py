@@ -280,20 +280,22 @@ STAGE_KERNELS = {"stft_fwd": "stft_", "istft_ola": "istft_", "dec_convT1_mask_xf
                  "score_channels": "channel_mul"}
 
 
-def workload_config(args, cpu=False, extra=None):
+def workload_config(args):
+    """The `config` of the JSON line: a function of the command line and WORLD_SIZE only, so that both arms
+    (`--impl ours`, `--impl reference`) print the SAME object for the same invocation.  What differs between
+    the arms (the reference arm's bounded sample; this arm's placement) goes into their own top-level keys."""
     c = args.cfg
-    d = {"workload": "%s, mono 44.1 kHz, frameSize=%d hop=512 time_context=30 overlap=%d, %s" % (
-            c["baseline"], c["N"], c["overlap"],
-            "bounded CPU sample" if cpu else "%d clips x %.0f s per step per GPU" % (args.clips, args.seconds)),
-         "name": args.config, "arch": c["arch"], "frame_size": c["N"], "hop": 512, "time_context": 30, "overlap": c["overlap"],
-         "window": c["window"], "patcher": c["patcher"], "nsrc": c["nsrc"],
-         "clips_per_step_per_gpu": args.clips, "clip_seconds": args.seconds,
-         "l2_policy": "inputs larger than L2 (%.0f MB of audio per step, intermediates of one clip exceed 126 MB)" % (
-             args.clips * args.seconds * SR * 4 / 1e6),
-         "parallelism": "clips sharded over %d GPU(s) (sharding.shard_clips), no data-path collective" % args.gpus}
-    if extra:
-        d.update(extra)
-    return d
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    return {"workload": "%s, mono 44.1 kHz, frameSize=%d hop=512 time_context=30 overlap=%d, %d clips x %.0f s per step per GPU" % (
+                c["baseline"], c["N"], c["overlap"], args.clips, args.seconds),
+            "name": args.config, "arch": c["arch"], "frame_size": c["N"], "hop": 512, "time_context": 30, "overlap": c["overlap"],
+            "window": c["window"], "patcher": c["patcher"], "nsrc": c["nsrc"],
+            "clips_per_step_per_gpu": args.clips, "clip_seconds": args.seconds,
+            "l2_policy": "inputs larger than L2 (%.0f MB of audio per step, intermediates of one clip exceed 126 MB)" % (
+                args.clips * args.seconds * SR * 4 / 1e6),
+            "parallelism": "clips sharded over %d GPU(s) (sharding.shard_clips), no data-path collective" % args.gpus,
+            "device_streams": max(1, args.device_streams),
+            "job": "%d clips sharded over %d rank(s)" % (world * args.clips, world)}
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
@@ -388,7 +390,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
         "warmup": W, "ms_per_step": dt / K * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, cpu=True, extra={"reference_clip_seconds": clip_s, "reference_workers": procs}),
+        "config": workload_config(args),
+        "reference_sample": {"clip_seconds": clip_s, "workers": procs, "clips_per_step": procs,
+                             "what": "each step is a bounded sample of the workload in `config`: one clip per worker"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample,
                          "single_process_value": single, "usable_host_threads": cores},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -713,8 +717,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, extra={"device_streams": nd, "numa": numa,
-                                                   "job": "%d clips sharded over %d rank(s)" % (world * B, world)}),
+            "config": workload_config(args), "placement": {"numa": numa},
             "x_realtime": value, "gpu_launches": int(launches), "outputs_finite": finite,
             "clocks": clocks, "parity": parity,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

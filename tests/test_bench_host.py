@@ -61,3 +61,17 @@ def test_bench_check_fixtures_are_consistent():
         assert g["mix"].dtype == np.int16 and g["stems"].shape == (bench.CONFIGS[name]["nsrc"], g["mix"].size)
         assert int(g["N"]) == bench.CONFIGS[name]["N"] and g["flag_t"].shape == g["flag_f"].shape
         assert g["S_or_flag"].shape == (bench.CONFIGS[name]["nsrc"], g["flag_t"].size)
+
+
+def test_both_arms_print_the_same_config(monkeypatch):
+    """`config` is a function of the command line and WORLD_SIZE only: the reference arm (launched by the driver
+    with the same flags, torchrun included) names the same workload as this arm; its bounded sample lives elsewhere."""
+    for extra, world in (([], "1"), (["--config", "bach10"], "1"), (["--gpus", "8"], "8")):
+        monkeypatch.setenv("WORLD_SIZE", world)
+        cfgs = []
+        for impl in ("ours", "reference"):
+            monkeypatch.setattr(sys, "argv", ["bench.py", "--impl", impl, "--steps", "20", "--warmup", "5"] + extra)
+            cfgs.append(bench.workload_config(bench.parse_args()))
+        assert cfgs[0] == cfgs[1]
+        assert cfgs[0]["job"] == "%d clips sharded over %s rank(s)" % (int(world) * cfgs[0]["clips_per_step_per_gpu"], world)
+        assert "L2" in cfgs[0]["l2_policy"] and "numa" not in cfgs[0]
